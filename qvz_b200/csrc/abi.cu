@@ -1,0 +1,455 @@
+// abi.cu -- extern "C" entry points of include/qvz_gpu.h.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "qvz_internal.cuh"
+
+#define QVZ_TARGET_RUNS (148u * 1024u)     // ~one resident quantize thread per run on a 148-SM B200
+
+enum { EV_A = 0, EV_B, EV_C, EV_D, EV_E, EV_F };
+
+static void free_dev(void *p) {
+	if (p) cudaFree(p);
+}
+
+static void release_rows(qvz_gpu *h) {
+	free_dev(h->Xw); h->Xw = nullptr;
+	free_dev(h->cl); h->cl = nullptr;
+	free_dev(h->run_states); h->run_states = nullptr;
+	free_dev(h->Yw); h->Yw = nullptr;
+	free_dev(h->Qw); h->Qw = nullptr;
+	free_dev(h->Ep); h->Ep = nullptr;
+	h->K = 0;
+}
+
+static void release_kmeans(qvz_gpu *h) {
+	free_dev(h->means_b); h->means_b = nullptr;
+	free_dev(h->means_w); h->means_w = nullptr;
+	free_dev(h->means_sq); h->means_sq = nullptr;
+	free_dev(h->sums); h->sums = nullptr;
+	free_dev(h->moved); h->moved = nullptr;
+	if (h->h_moved) cudaFreeHost(h->h_moved);
+	if (h->h_counts) cudaFreeHost(h->h_counts);
+	h->h_moved = nullptr;
+	h->h_counts = nullptr;
+	h->km_K = 0;
+}
+
+static float ev_ms(qvz_gpu *h, int a, int b) {
+	float ms = 0.f;
+	cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]);
+	return ms;
+}
+
+// read-and-clear one device flag (after the stream has been synchronised)
+static int take_flag(qvz_gpu *h, int idx, int *value) {
+	QVZ_CUDA(h, cudaMemcpyAsync(h->h_flags, h->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+	*value = h->h_flags[idx];
+	if (*value) {
+		h->h_flags[idx] = 0;
+		QVZ_CUDA(h, cudaMemcpyAsync(h->flags + idx, h->h_flags + idx, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+		QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+	}
+	return QVZ_OK;
+}
+
+extern "C" int qvz_gpu_open(qvz_gpu **out, int device) {
+	if (!out) return QVZ_ERR_ARG;
+	*out = nullptr;
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return QVZ_ERR_CUDA;
+	qvz_gpu *h = (qvz_gpu *) calloc(1, sizeof(qvz_gpu));
+	if (!h) return QVZ_ERR_ARG;
+	h->device = device;
+	*out = h;       // returned even on failure below so the caller can read last_error, then close
+	QVZ_CUDA(h, cudaSetDevice(device));
+	QVZ_CUDA(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+	QVZ_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 8; ++i) QVZ_CUDA(h, cudaEventCreate(&h->ev[i]));
+	QVZ_CUDA(h, cudaMalloc(&h->flags, 4 * sizeof(int)));
+	QVZ_CUDA(h, cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
+	QVZ_CUDA(h, cudaMallocHost(&h->h_flags, 4 * sizeof(int)));
+	QVZ_CUDA(h, cudaMalloc(&h->D, 72 * 72 * sizeof(double)));
+	return qvz_well_init(h);
+}
+
+extern "C" void qvz_gpu_close(qvz_gpu *h) {
+	if (!h) return;
+	cudaSetDevice(h->device);
+	if (h->stream) cudaStreamSynchronize(h->stream);
+	release_rows(h);
+	release_kmeans(h);
+	qvz_well_free(h);
+	free_dev(h->U);
+	free_dev(h->R);
+	free_dev(h->D);
+	free_dev(h->flags);
+	if (h->h_flags) cudaFreeHost(h->h_flags);
+	for (int i = 0; i < 8; ++i)
+		if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+	if (h->stream) cudaStreamDestroy(h->stream);
+	free(h);
+}
+
+extern "C" const char *qvz_gpu_last_error(const qvz_gpu *h) { return h ? h->err : "null handle"; }
+extern "C" void *qvz_gpu_stream(qvz_gpu *h) { return h ? (void *) h->stream : nullptr; }
+
+extern "C" int qvz_gpu_get_timings(qvz_gpu *h, struct qvz_gpu_timings *out) {
+	if (!h || !out) return QVZ_ERR_ARG;
+	*out = h->tm;
+	return QVZ_OK;
+}
+
+extern "C" int qvz_gpu_reset_launch_count(qvz_gpu *h) {
+	if (!h) return QVZ_ERR_ARG;
+	h->tm.kernel_launches = 0;
+	return QVZ_OK;
+}
+
+extern "C" uint64_t qvz_gpu_cond_counts_len(uint32_t K, uint32_t columns) {
+	return (uint64_t) K * (1 + (uint64_t) QVZ_ALPHABET * (columns - 1)) * QVZ_ALPHABET;
+}
+
+// ------------------------------------------------------------------------------------------ ingest
+extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lines, uint32_t columns,
+                                 uint32_t row_stride, uint64_t first_line)
+{
+	if (!h || !rows) return QVZ_ERR_ARG;
+	if (n_lines == 0 || columns == 0 || columns > QVZ_MAX_COLUMNS || row_stride < columns)
+		QVZ_FAIL(h, QVZ_ERR_ARG, "load_rows: need n_lines > 0, 0 < columns <= %u, row_stride >= columns", QVZ_MAX_COLUMNS);
+	if (first_line & 3) QVZ_FAIL(h, QVZ_ERR_ARG, "load_rows: first_line must be a multiple of 4");
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	release_rows(h);
+
+	qvz_layout &L = h->L;
+	L.n_lines = n_lines;
+	L.first_line = first_line;
+	L.C = columns;
+	L.C4 = (columns + 3) / 4;
+	uint64_t lr = (n_lines + QVZ_TARGET_RUNS - 1) / QVZ_TARGET_RUNS;
+	lr = (lr + 3) & ~3ull;
+	if (lr < 4) lr = 4;
+	L.Lr = (uint32_t) lr;
+	uint64_t runs = (n_lines + lr - 1) / lr;
+	L.T = (uint32_t) ((runs + QVZ_THREADS - 1) / QVZ_THREADS * QVZ_THREADS);
+	L.P = (uint64_t) L.T * L.Lr;
+
+	uint8_t *raw = nullptr;
+	const size_t raw_bytes = (size_t) ((n_lines - 1) * (uint64_t) row_stride + columns);
+	QVZ_CUDA(h, cudaMalloc(&raw, raw_bytes));
+	QVZ_CUDA(h, cudaMalloc(&h->Xw, (size_t) L.C4 * L.P * sizeof(uint32_t)));
+	QVZ_CUDA(h, cudaMalloc(&h->cl, (size_t) L.P));
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(raw, rows, raw_bytes, cudaMemcpyHostToDevice, h->stream));
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
+	int rc = qvz_layout_ingest(h, raw, row_stride);
+	if (rc) {
+		cudaFree(raw);
+		return rc;
+	}
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));
+	int bad = 0;
+	rc = take_flag(h, 0, &bad);
+	cudaFree(raw);
+	if (rc) return rc;
+	h->tm.load_h2d_ms = ev_ms(h, EV_A, EV_B);
+	h->tm.load_layout_ms = ev_ms(h, EV_B, EV_C);
+	if (bad) {
+		release_rows(h);
+		QVZ_FAIL(h, QVZ_ERR_SYMBOL_RANGE, "load_rows: a quality byte is outside ['!', '!'+71]");
+	}
+	return QVZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------ k-means
+extern "C" int qvz_gpu_kmeans_begin(qvz_gpu *h, uint32_t K, const uint8_t *init_means) {
+	if (!h || !init_means) return QVZ_ERR_ARG;
+	if (!h->Xw) QVZ_FAIL(h, QVZ_ERR_ARG, "kmeans: no rows loaded");
+	if (K == 0 || K > QVZ_MAX_K) QVZ_FAIL(h, QVZ_ERR_UNSUPPORTED, "kmeans: 1 <= clusters <= %d supported", QVZ_MAX_K);
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	release_kmeans(h);
+	const uint32_t C = h->L.C, C4 = h->L.C4;
+	h->km_K = K;
+	QVZ_CUDA(h, cudaMalloc(&h->means_b, (size_t) K * C));
+	QVZ_CUDA(h, cudaMalloc(&h->means_w, (size_t) K * C4 * sizeof(uint32_t)));
+	QVZ_CUDA(h, cudaMalloc(&h->means_sq, K * sizeof(uint32_t)));
+	QVZ_CUDA(h, cudaMalloc(&h->sums, ((size_t) K * C + K) * sizeof(int64_t)));
+	QVZ_CUDA(h, cudaMalloc(&h->moved, K * sizeof(double)));
+	QVZ_CUDA(h, cudaMallocHost(&h->h_moved, K * sizeof(double)));
+	QVZ_CUDA(h, cudaMallocHost(&h->h_counts, K * sizeof(uint32_t)));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->means_b, init_means, (size_t) K * C, cudaMemcpyHostToDevice, h->stream));
+	h->K = K;
+	return qvz_kmeans_launch_update(h, nullptr);     // pack the initial centroids
+}
+
+extern "C" int qvz_gpu_kmeans_assign_dev(qvz_gpu *h, int64_t *sums_dev) {
+	if (!h || !sums_dev || !h->km_K) return QVZ_ERR_ARG;
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	return qvz_kmeans_launch_assign(h, sums_dev);
+}
+
+extern "C" int qvz_gpu_kmeans_update_dev(qvz_gpu *h, const int64_t *sums_dev, double *moved_out, uint32_t *counts_out) {
+	if (!h || !sums_dev || !h->km_K) return QVZ_ERR_ARG;
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	const uint32_t K = h->km_K, C = h->L.C;
+	int rc = qvz_kmeans_launch_update(h, sums_dev);
+	if (rc) return rc;
+	std::vector<int64_t> cnt(K);
+	QVZ_CUDA(h, cudaMemcpyAsync(h->h_moved, h->moved, K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(cnt.data(), sums_dev + (size_t) K * C, K * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+	int empty = 0;
+	rc = take_flag(h, 1, &empty);                    // synchronises the stream
+	if (rc) return rc;
+	for (uint32_t k = 0; k < K; ++k) {
+		if (moved_out) moved_out[k] = h->h_moved[k];
+		if (counts_out) counts_out[k] = (uint32_t) cnt[k];
+	}
+	if (empty) QVZ_FAIL(h, QVZ_ERR_EMPTY_CLUSTER, "kmeans: a cluster has no lines (the reference divides by zero, src/cluster.c:113)");
+	return QVZ_OK;
+}
+
+static int ids_to_host(qvz_gpu *h, uint8_t *ids_out) {
+	uint8_t *ids_dev = nullptr;
+	QVZ_CUDA(h, cudaMalloc(&ids_dev, (size_t) h->L.n_lines));
+	int rc = qvz_layout_ids_to_lines(h, ids_dev);
+	if (!rc) {
+		cudaError_t e = cudaMemcpyAsync(ids_out, ids_dev, (size_t) h->L.n_lines, cudaMemcpyDeviceToHost, h->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+		if (e != cudaSuccess) {
+			snprintf(h->err, sizeof(h->err), "ids D2H: %s", cudaGetErrorString(e));
+			rc = QVZ_ERR_CUDA;
+		}
+	}
+	cudaFree(ids_dev);
+	return rc;
+}
+
+extern "C" int qvz_gpu_kmeans_end(qvz_gpu *h, uint8_t *cluster_ids_out, uint8_t *means_out) {
+	if (!h || !h->km_K) return QVZ_ERR_ARG;
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	if (means_out) {
+		QVZ_CUDA(h, cudaMemcpyAsync(means_out, h->means_b, (size_t) h->km_K * h->L.C, cudaMemcpyDeviceToHost, h->stream));
+		QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+	}
+	if (cluster_ids_out) return ids_to_host(h, cluster_ids_out);
+	return QVZ_OK;
+}
+
+extern "C" int qvz_gpu_kmeans(qvz_gpu *h, uint32_t K, const uint8_t *init_means, double threshold,
+                              uint32_t max_iter, uint8_t *cluster_ids_out, uint8_t *means_out,
+                              uint32_t *counts_out, double *moved_log_out, uint32_t *iters_out)
+{
+	int rc = qvz_gpu_kmeans_begin(h, K, init_means);
+	if (rc) return rc;
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
+	std::vector<double> moved(K);
+	uint32_t iter = 0;
+	bool loop = true;
+	float assign_ms = 0.f;
+	// do_kmeans_clustering: while (iter_count < MAX_KMEANS_ITERATIONS && loop)  (src/cluster.c:221)
+	while (iter < max_iter && loop) {
+		QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));
+		rc = qvz_gpu_kmeans_assign_dev(h, h->sums);
+		if (rc) return rc;
+		QVZ_CUDA(h, cudaEventRecord(h->ev[EV_D], h->stream));
+		rc = qvz_gpu_kmeans_update_dev(h, h->sums, moved.data(), counts_out);
+		if (rc) return rc;
+		assign_ms += ev_ms(h, EV_C, EV_D);
+		double move_max = 0.0;
+		for (uint32_t k = 0; k < K; ++k) {
+			if (moved[k] > move_max) move_max = moved[k];
+			if (moved_log_out) moved_log_out[(size_t) iter * K + k] = moved[k];
+		}
+		loop = move_max > threshold;             // src/cluster.c:231-233
+		iter += 1;
+	}
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
+	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+	h->tm.kmeans_ms = ev_ms(h, EV_A, EV_B);
+	h->tm.kmeans_assign_ms = assign_ms;
+	h->tm.kmeans_iters = iter;
+	if (iters_out) *iters_out = iter;
+	return qvz_gpu_kmeans_end(h, cluster_ids_out, means_out);
+}
+
+extern "C" int qvz_gpu_set_clusters(qvz_gpu *h, uint32_t K, const uint8_t *cluster_ids) {
+	if (!h || !cluster_ids) return QVZ_ERR_ARG;
+	if (!h->Xw) QVZ_FAIL(h, QVZ_ERR_ARG, "set_clusters: no rows loaded");
+	if (K == 0 || K > 255) QVZ_FAIL(h, QVZ_ERR_ARG, "set_clusters: bad cluster count");
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	uint8_t *ids_dev = nullptr;
+	QVZ_CUDA(h, cudaMalloc(&ids_dev, (size_t) h->L.n_lines));
+	cudaError_t e = cudaMemcpyAsync(ids_dev, cluster_ids, (size_t) h->L.n_lines, cudaMemcpyHostToDevice, h->stream);
+	int rc = QVZ_OK;
+	if (e == cudaSuccess) rc = qvz_layout_ids_from_lines(h, ids_dev);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+	cudaFree(ids_dev);
+	if (e != cudaSuccess) QVZ_FAIL(h, QVZ_ERR_CUDA, "set_clusters: %s", cudaGetErrorString(e));
+	if (!rc) h->K = K;
+	return rc;
+}
+
+// ------------------------------------------------------------------------------------------ counts
+extern "C" int qvz_gpu_cond_counts_dev(qvz_gpu *h, uint32_t *counts_dev) {
+	if (!h || !counts_dev) return QVZ_ERR_ARG;
+	if (!h->Xw || !h->K) QVZ_FAIL(h, QVZ_ERR_ARG, "cond_counts: rows and cluster ids must be resident first");
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
+	int rc = qvz_cond_counts_launch(h, counts_dev);
+	if (rc) return rc;
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
+	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+	h->tm.cond_counts_ms = ev_ms(h, EV_A, EV_B);
+	return QVZ_OK;
+}
+
+extern "C" int qvz_gpu_cond_counts(qvz_gpu *h, uint32_t *counts_out) {
+	if (!h) return QVZ_ERR_ARG;
+	if (!h->Xw || !h->K) QVZ_FAIL(h, QVZ_ERR_ARG, "cond_counts: rows and cluster ids must be resident first");
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	const size_t bytes = (size_t) qvz_gpu_cond_counts_len(h->K, h->L.C) * sizeof(uint32_t);
+	uint32_t *dev = nullptr;
+	QVZ_CUDA(h, cudaMalloc(&dev, bytes));
+	int rc = qvz_gpu_cond_counts_dev(h, dev);
+	if (!rc && counts_out) {
+		cudaError_t e = cudaMemcpyAsync(counts_out, dev, bytes, cudaMemcpyDeviceToHost, h->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+		if (e != cudaSuccess) {
+			snprintf(h->err, sizeof(h->err), "cond_counts D2H: %s", cudaGetErrorString(e));
+			rc = QVZ_ERR_CUDA;
+		}
+	}
+	cudaFree(dev);
+	return rc;
+}
+
+// ------------------------------------------------------------------------------------------ quantize
+// Compose ctx_of -> (qmap, smap) into U / R (see quantize.cu) on the host and upload.
+static int upload_tables(qvz_gpu *h, const struct qvz_flat_tables *t) {
+	const uint32_t K = t->clusters, C = t->columns;
+	const size_t rows = (size_t) K * C * 72;
+	const size_t u_elems = rows * 2 * 72;
+	std::vector<uint16_t> U(u_elems, 0);
+	std::vector<uint8_t> R(rows, 0xFF);
+	for (size_t kc = 0; kc < (size_t) K * C; ++kc) {
+		if (t->nctx[kc] > 72 || (t->q_off[kc] & 1)) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: malformed flat tables");
+		for (uint32_t v = 0; v < 72; ++v) {
+			const uint32_t ctx = t->ctx_of[kc * 72 + v];
+			if (ctx == QVZ_CTX_ABSENT) continue;
+			if (ctx >= t->nctx[kc]) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: context index out of range");
+			R[kc * 72 + v] = t->qratio[t->q_off[kc] / 2 + ctx];
+			for (uint32_t hi = 0; hi < 2; ++hi) {
+				const uint8_t *qm = t->qmap + (t->q_off[kc] + 2 * ctx + hi) * 72;
+				const uint8_t *sm = t->smap + (t->q_off[kc] + 2 * ctx + hi) * 72;
+				uint16_t *dst = &U[((kc * 72 + v) * 2 + hi) * 72];
+				for (uint32_t x = 0; x < 72; ++x) {
+					const uint32_t qv = qm[x];
+					if (qv >= 72) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: quantized value out of range");
+					dst[x] = (uint16_t) ((sm[qv] & 0x7F) | (qv << 8));
+				}
+			}
+		}
+	}
+	if (h->U_cap < u_elems * sizeof(uint16_t)) {
+		free_dev(h->U);
+		h->U = nullptr;
+		QVZ_CUDA(h, cudaMalloc(&h->U, u_elems * sizeof(uint16_t)));
+		h->U_cap = u_elems * sizeof(uint16_t);
+	}
+	if (h->R_cap < rows) {
+		free_dev(h->R);
+		h->R = nullptr;
+		QVZ_CUDA(h, cudaMalloc(&h->R, rows));
+		h->R_cap = rows;
+	}
+	QVZ_CUDA(h, cudaMemcpyAsync(h->U, U.data(), u_elems * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->R, R.data(), rows, cudaMemcpyHostToDevice, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->D, t->distortion, 72 * 72 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));       // U/R are function-local host buffers
+	return QVZ_OK;
+}
+
+extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, const uint32_t well_seed[32],
+                                uint8_t *symbols_out, uint8_t *qv_out, double *line_err_out)
+{
+	if (!h || !t || !well_seed) return QVZ_ERR_ARG;
+	if (!h->Xw || !h->K) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: rows and cluster ids must be resident first");
+	if (t->columns != h->L.C || t->clusters < h->K)
+		QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: tables are for %u clusters x %u columns, data has %u x %u", t->clusters, t->columns, h->K, h->L.C);
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	const qvz_layout &L = h->L;
+	const size_t wbytes = (size_t) L.C4 * L.P * sizeof(uint32_t);
+	if (!h->Yw) QVZ_CUDA(h, cudaMalloc(&h->Yw, wbytes));
+	if (qv_out && !h->Qw) QVZ_CUDA(h, cudaMalloc(&h->Qw, wbytes));
+	if (line_err_out && !h->Ep) QVZ_CUDA(h, cudaMalloc(&h->Ep, (size_t) L.P * sizeof(double)));
+	if (!h->run_states) QVZ_CUDA(h, cudaMalloc(&h->run_states, (size_t) L.T * 32 * sizeof(uint32_t)));
+
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
+	int rc = upload_tables(h, t);
+	if (rc) return rc;
+	rc = qvz_well_run_states(h, well_seed);
+	if (rc) return rc;
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
+	rc = qvz_quantize_launch(h, qv_out != nullptr, line_err_out != nullptr);
+	if (rc) return rc;
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));
+
+	// egress: packed -> line-major on the device, then D2H
+	uint8_t *out_dev = nullptr;
+	double *err_dev = nullptr;
+	cudaError_t e = cudaSuccess;
+	if (symbols_out) {
+		const size_t bytes = (size_t) L.n_lines * L.C;
+		QVZ_CUDA(h, cudaMalloc(&out_dev, bytes));
+		rc = qvz_layout_words_to_lines(h, h->Yw, out_dev, L.C, 0);
+		if (!rc) e = cudaMemcpyAsync(symbols_out, out_dev, bytes, cudaMemcpyDeviceToHost, h->stream);
+		if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+		cudaFree(out_dev);
+		out_dev = nullptr;
+	}
+	if (!rc && e == cudaSuccess && qv_out) {
+		const size_t bytes = (size_t) L.n_lines * (L.C + 1);
+		e = cudaMalloc(&out_dev, bytes);
+		if (e == cudaSuccess) rc = qvz_layout_words_to_lines(h, h->Qw, out_dev, L.C + 1, 1);
+		if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(qv_out, out_dev, bytes, cudaMemcpyDeviceToHost, h->stream);
+		if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+		if (out_dev) cudaFree(out_dev);
+	}
+	if (!rc && e == cudaSuccess && line_err_out) {
+		e = cudaMalloc(&err_dev, (size_t) L.n_lines * sizeof(double));
+		if (e == cudaSuccess) rc = qvz_layout_doubles_to_lines(h, h->Ep, err_dev);
+		if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(line_err_out, err_dev, (size_t) L.n_lines * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+		if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+		if (err_dev) cudaFree(err_dev);
+	}
+	if (rc) return rc;
+	if (e != cudaSuccess) QVZ_FAIL(h, QVZ_ERR_CUDA, "quantize egress: %s", cudaGetErrorString(e));
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_D], h->stream));
+	int missing = 0;
+	rc = take_flag(h, 2, &missing);
+	if (rc) return rc;
+	h->tm.quantize_setup_ms = ev_ms(h, EV_A, EV_B);
+	h->tm.quantize_ms = ev_ms(h, EV_B, EV_C);
+	h->tm.quantize_d2h_ms = ev_ms(h, EV_C, EV_D);
+	if (missing) QVZ_FAIL(h, QVZ_ERR_CONTEXT, "quantize: reached a context without a quantizer (the reference asserts, src/codebook.c:164)");
+	return QVZ_OK;
+}
+
+extern "C" int qvz_gpu_well_jump(qvz_gpu *h, const uint32_t seed[32], uint64_t words, uint32_t state_out[32]) {
+	if (!h || !seed || !state_out) return QVZ_ERR_ARG;
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	uint32_t *dev = nullptr;
+	QVZ_CUDA(h, cudaMalloc(&dev, 32 * sizeof(uint32_t)));
+	int rc = qvz_well_jump_state(h, seed, words, dev);
+	cudaError_t e = cudaSuccess;
+	if (!rc) e = cudaMemcpyAsync(state_out, dev, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream);
+	if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+	cudaFree(dev);
+	if (rc) return rc;
+	if (e != cudaSuccess) QVZ_FAIL(h, QVZ_ERR_CUDA, "well_jump: %s", cudaGetErrorString(e));
+	return QVZ_OK;
+}

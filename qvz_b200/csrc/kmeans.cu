@@ -1,0 +1,194 @@
+// kmeans.cu -- one k-means iteration as one fused pass over the resident rows.
+//
+// Reference (src/cluster.c): cluster_lines (:65-74) -> do_cluster_assignment (:136-144) ->
+// find_distance (:176-187) + assign_cluster (:149-171), then recalculate_means (:80-131), which walks
+// all rows a second time.  Here both happen in one kernel launch per iteration:
+//
+//   distance:  find_distance sums uint32 squares into a double; every partial sum is an integer
+//              < 2^53 so integer arithmetic gives the same values and the same '<' outcomes.
+//              argmin_k sum (x-m_k)^2  =  argmin_k ( sum m_k^2  -  2 * sum x*m_k )   (sum x^2 is common),
+//              and sum x*m_k over 4 columns is one dp4a on the packed words.  Ties: strict '<' in
+//              cluster order => lowest id wins, as in assign_cluster.
+//   sums:      accumulator[cluster][col] += byte  (uint64 in the reference) -> warp REDUX of the packed
+//              16-bit fields per (cluster, word), CTA-level uint32 partials in shared memory, one
+//              64-bit global atomic per (cluster, column, CTA).  Integer sums are order independent.
+//   recenter:  mean = (uint8)(sum / count), moved_k = sum (new-old)^2 -- tiny second kernel.
+#include "qvz_internal.cuh"
+
+template <int KT>
+__global__ void __launch_bounds__(QVZ_THREADS)
+qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t *__restrict__ cl,
+                         const uint32_t *__restrict__ means_w, const uint32_t *__restrict__ means_sq,
+                         uint32_t Krt, unsigned long long *__restrict__ sums)
+{
+	const uint32_t K = KT > 0 ? (uint32_t) KT : Krt;
+	const uint32_t C4 = L.C4;
+	extern __shared__ uint32_t sm[];
+	uint32_t *mean_s = sm;                       // [K][C4]
+	uint32_t *acc = mean_s + K * C4;             // [K][C4*4]
+	uint32_t *cnt = acc + K * C4 * 4;            // [K]
+	uint32_t *msq = cnt + K;                     // [K]
+
+	for (uint32_t i = threadIdx.x; i < K * C4; i += QVZ_THREADS) mean_s[i] = means_w[i];
+	for (uint32_t i = threadIdx.x; i < K * C4 * 4; i += QVZ_THREADS) acc[i] = 0;
+	if (threadIdx.x < K) {
+		cnt[threadIdx.x] = 0;
+		msq[threadIdx.x] = means_sq[threadIdx.x];
+	}
+	__syncthreads();
+
+	const uint32_t lane = threadIdx.x & 31;
+	for (uint64_t base = (uint64_t) blockIdx.x * QVZ_THREADS; base < L.P; base += (uint64_t) gridDim.x * QVZ_THREADS) {
+		const uint64_t p = base + threadIdx.x;       // P is a multiple of QVZ_THREADS: whole warps stay active
+		const bool valid = cl[p] != QVZ_NO_LINE;
+		uint32_t best = 0;
+		if (K > 1) {
+			uint32_t D[KT > 0 ? KT : QVZ_MAX_K];
+#pragma unroll
+			for (int k = 0; k < (KT > 0 ? KT : QVZ_MAX_K); ++k) D[k] = 0;
+			for (uint32_t c4 = 0; c4 < C4; ++c4) {
+				const uint32_t w = Xw[(uint64_t) c4 * L.P + p];
+#pragma unroll
+				for (int k = 0; k < (KT > 0 ? KT : QVZ_MAX_K); ++k)
+					if (KT > 0 || (uint32_t) k < K) D[k] = __dp4a(w, mean_s[k * C4 + c4], D[k]);
+			}
+			int bestv = (int) msq[0] - 2 * (int) D[0];
+#pragma unroll
+			for (int k = 1; k < (KT > 0 ? KT : QVZ_MAX_K); ++k) {
+				if (KT > 0 || (uint32_t) k < K) {
+					const int v = (int) msq[k] - 2 * (int) D[k];
+					if (v < bestv) {
+						bestv = v;
+						best = k;
+					}
+				}
+			}
+		}
+		if (valid) cl[p] = (uint8_t) best;
+
+		// column sums of this warp's 32 rows, per cluster (slots without a line hold zero words)
+		for (uint32_t c4 = 0; c4 < C4; ++c4) {
+			const uint32_t w = Xw[(uint64_t) c4 * L.P + p];
+			const uint32_t lo = w & 0x00FF00FFu, hi = (w >> 8) & 0x00FF00FFu;
+			for (uint32_t k = 0; k < K; ++k) {
+				const bool mine = (K == 1) || (best == k);
+				const uint32_t slo = __reduce_add_sync(0xFFFFFFFFu, mine ? lo : 0u);
+				const uint32_t shi = __reduce_add_sync(0xFFFFFFFFu, mine ? hi : 0u);
+				if (lane < 4) {
+					const uint32_t pair = (lane & 1) ? shi : slo;            // bytes 1,3 live in hi; 0,2 in lo
+					const uint32_t f = (lane & 2) ? (pair >> 16) : (pair & 0xFFFFu);
+					if (f) atomicAdd(&acc[(k * C4 + c4) * 4 + lane], f);
+				}
+			}
+		}
+		for (uint32_t k = 0; k < K; ++k) {
+			const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, valid && best == k));
+			if (lane == 0 && n) atomicAdd(&cnt[k], n);
+		}
+	}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < K * C4 * 4; i += QVZ_THREADS) {
+		const uint32_t k = i / (C4 * 4), c = i - k * C4 * 4;
+		if (c < L.C && acc[i]) atomicAdd(&sums[(uint64_t) k * L.C + c], (unsigned long long) acc[i]);
+	}
+	if (threadIdx.x < K && cnt[threadIdx.x])
+		atomicAdd(&sums[(uint64_t) K * L.C + threadIdx.x], (unsigned long long) cnt[threadIdx.x]);
+}
+
+// recalculate_means (src/cluster.c:106-128) on the reduced sums; also repacks the centroids for dp4a.
+// first = 1: only pack the initial centroids (initialize_kmeans_clustering copied them from rows).
+__global__ void __launch_bounds__(QVZ_THREADS)
+qvz_kmeans_update_kernel(uint32_t K, uint32_t C, uint32_t C4, const unsigned long long *__restrict__ sums,
+                         uint8_t *__restrict__ means_b, uint32_t *__restrict__ means_w,
+                         uint32_t *__restrict__ means_sq, double *__restrict__ moved,
+                         int *__restrict__ flags, int first)
+{
+	__shared__ unsigned long long red_moved[QVZ_THREADS / 32];
+	__shared__ unsigned long long red_sq[QVZ_THREADS / 32];
+	for (uint32_t k = 0; k < K; ++k) {
+		unsigned long long count = first ? 1ull : sums[(uint64_t) K * C + k];
+		if (count == 0) {
+			if (threadIdx.x == 0) atomicOr(&flags[1], 1);
+			count = 1;
+		}
+		unsigned long long mv = 0, sq = 0;
+		for (uint32_t c = threadIdx.x; c < C; c += QVZ_THREADS) {
+			const uint32_t old = means_b[k * C + c];
+			uint32_t nm = old;
+			if (!first) {
+				nm = (uint32_t) (sums[(uint64_t) k * C + c] / count) & 0xFFu;   // (uint8_t)(acc/count)
+				const int d = (int) nm - (int) old;
+				mv += (unsigned long long) (d * d);
+				means_b[k * C + c] = (uint8_t) nm;
+			}
+			sq += (unsigned long long) nm * nm;
+		}
+		for (int o = 16; o > 0; o >>= 1) {
+			mv += __shfl_down_sync(0xFFFFFFFFu, mv, o);
+			sq += __shfl_down_sync(0xFFFFFFFFu, sq, o);
+		}
+		if ((threadIdx.x & 31) == 0) {
+			red_moved[threadIdx.x >> 5] = mv;
+			red_sq[threadIdx.x >> 5] = sq;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			unsigned long long a = 0, b = 0;
+			for (int w = 0; w < QVZ_THREADS / 32; ++w) {
+				a += red_moved[w];
+				b += red_sq[w];
+			}
+			if (!first) moved[k] = (double) a;       // exact: an integer < 2^53, like the reference's double sum
+			means_sq[k] = (uint32_t) b;
+		}
+		__syncthreads();
+		for (uint32_t c4 = threadIdx.x; c4 < C4; c4 += QVZ_THREADS) {
+			uint32_t w = 0;
+			for (uint32_t j = 0; j < 4; ++j)
+				if (4 * c4 + j < C) w |= (uint32_t) means_b[k * C + 4 * c4 + j] << (8 * j);
+			means_w[k * C4 + c4] = w;
+		}
+		__syncthreads();
+	}
+}
+
+template <int KT>
+static void launch_assign(qvz_gpu *h, int64_t *sums_dev, unsigned grid, size_t smem) {
+	auto kern = qvz_kmeans_assign_kernel<KT>;
+	if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	kern<<<grid, QVZ_THREADS, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K,
+	                                             (unsigned long long *) sums_dev);
+}
+
+int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev) {
+	const uint32_t K = h->km_K, C4 = h->L.C4;
+	const size_t smem = ((size_t) K * C4 * 5 + 2 * K) * sizeof(uint32_t);
+	if (smem > 200 * 1024) QVZ_FAIL(h, QVZ_ERR_UNSUPPORTED, "k-means: K*columns too large for shared memory");
+	uint64_t blocks = h->L.P / QVZ_THREADS;
+	const uint64_t cap = (uint64_t) h->sm_count * 8;
+	const unsigned grid = (unsigned) (blocks < cap ? blocks : cap);
+	QVZ_CUDA(h, cudaMemsetAsync(sums_dev, 0, ((size_t) K * h->L.C + K) * sizeof(int64_t), h->stream));
+	switch (K) {
+	case 1: launch_assign<1>(h, sums_dev, grid, smem); break;
+	case 2: launch_assign<2>(h, sums_dev, grid, smem); break;
+	case 3: launch_assign<3>(h, sums_dev, grid, smem); break;
+	case 4: launch_assign<4>(h, sums_dev, grid, smem); break;
+	case 5: launch_assign<5>(h, sums_dev, grid, smem); break;
+	case 6: launch_assign<6>(h, sums_dev, grid, smem); break;
+	case 7: launch_assign<7>(h, sums_dev, grid, smem); break;
+	case 8: launch_assign<8>(h, sums_dev, grid, smem); break;
+	default: launch_assign<0>(h, sums_dev, grid, smem); break;
+	}
+	QVZ_LAUNCHED(h);
+	QVZ_CUDA(h, cudaGetLastError());
+	return QVZ_OK;
+}
+
+int qvz_kmeans_launch_update(qvz_gpu *h, const int64_t *sums_dev) {
+	qvz_kmeans_update_kernel<<<1, QVZ_THREADS, 0, h->stream>>>(
+	    h->km_K, h->L.C, h->L.C4, (const unsigned long long *) sums_dev, h->means_b, h->means_w,
+	    h->means_sq, h->moved, h->flags, sums_dev == nullptr);
+	QVZ_LAUNCHED(h);
+	QVZ_CUDA(h, cudaGetLastError());
+	return QVZ_OK;
+}

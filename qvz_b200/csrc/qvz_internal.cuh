@@ -1,0 +1,121 @@
+// qvz_internal.cuh -- shared declarations of the B200 (sm_100a) qvz front end.
+//
+// Device-resident data layout:
+//
+//   slot p  <->  line n :   the shard's lines are cut into T "runs" of Lr consecutive lines
+//                           (Lr % 4 == 0 so that every run starts on a WELL word boundary);
+//                           run r, step i  =  line r*Lr + i  =  slot p = i*T + r.
+//                           Thread r of the quantize kernel walks run r sequentially, so its WELL1024a
+//                           stream is one contiguous piece of the reference's draw stream, while
+//                           adjacent threads touch adjacent slots => every access below is coalesced.
+//   Xw[c4][p]  uint32       bytes 4*c4 .. 4*c4+3 of the line in slot p (raw ASCII, '\n' stripped,
+//                           zero padded past the last column / past the last line)
+//   cl[p]      uint8        cluster id of slot p (0xFF = slot holds no line)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/qvz_gpu.h"
+
+#define QVZ_THREADS 256
+#define QVZ_NO_LINE 0xFFu
+#define QVZ_MAX_K 16            // register-resident distances in the k-means kernel
+
+struct qvz_layout {
+	uint64_t n_lines;    // lines in this shard
+	uint64_t first_line; // global index of line 0 of the shard
+	uint32_t C;          // columns
+	uint32_t C4;         // ceil(C/4) words per line
+	uint32_t Lr;         // lines per run (multiple of 4)
+	uint32_t T;          // runs (multiple of QVZ_THREADS)
+	uint64_t P;          // slots = T * Lr
+};
+
+static __host__ __device__ __forceinline__ uint64_t qvz_slot_line(const qvz_layout &L, uint64_t p) {
+	uint64_t i = p / L.T, r = p - i * L.T;
+	return r * L.Lr + i;
+}
+
+struct qvz_well_cache;   // well.cu
+
+struct qvz_gpu {
+	int device;
+	cudaStream_t stream;
+	char err[512];
+	int sm_count;
+
+	qvz_layout L;
+	uint32_t *Xw;            // [C4][P]
+	uint8_t *cl;             // [P]
+	uint32_t K;              // clusters currently installed in cl (0 = none)
+	int *flags;              // device: [0] symbol range, [1] empty cluster, [2] missing context
+	int *h_flags;            // pinned mirror
+
+	// k-means state
+	uint32_t km_K;
+	uint8_t *means_b;        // [K][C] current centroids (raw ASCII bytes)
+	uint32_t *means_w;       // [K][C4] same, packed for dp4a (zero padded)
+	uint32_t *means_sq;      // [K] sum of squares of each centroid
+	int64_t *sums;           // [K*C + K] column sums, then line counts
+	double *moved;           // [K] device
+	double *h_moved;         // pinned [K]
+	uint32_t *h_counts;      // pinned [K]
+
+	// quantize state
+	uint16_t *U;             // [K][C][72 prev][2 hi][72 data] -> state | qv << 8
+	uint8_t *R;              // [K][C][72 prev] qratio, 0xFF = no such context
+	double *D;               // [72*72]
+	size_t U_cap, R_cap;
+	uint32_t *run_states;    // [T][32] WELL state (n = 0 frame) at the first draw of each run
+	uint32_t *Yw, *Qw;       // [C4][P] packed outputs (state|hi<<7, qv+33)
+	double *Ep;              // [P] per-slot error / C
+	qvz_well_cache *well;
+
+	// events / timings
+	cudaEvent_t ev[8];
+	qvz_gpu_timings tm;
+};
+
+#define QVZ_CUDA(h, call)                                                                         \
+	do {                                                                                          \
+		cudaError_t e__ = (call);                                                                 \
+		if (e__ != cudaSuccess) {                                                                 \
+			snprintf((h)->err, sizeof((h)->err), "%s:%d: %s: %s", __FILE__, __LINE__, #call,      \
+			         cudaGetErrorString(e__));                                                    \
+			return QVZ_ERR_CUDA;                                                                  \
+		}                                                                                         \
+	} while (0)
+
+#define QVZ_FAIL(h, code, ...)                                                                    \
+	do {                                                                                          \
+		snprintf((h)->err, sizeof((h)->err), __VA_ARGS__);                                        \
+		return (code);                                                                            \
+	} while (0)
+
+#define QVZ_LAUNCHED(h) ((h)->tm.kernel_launches += 1)
+
+// layout.cu
+int qvz_layout_ingest(qvz_gpu *h, const uint8_t *raw_dev, uint32_t row_stride);
+int qvz_layout_ids_to_lines(qvz_gpu *h, uint8_t *ids_dev /* [n_lines] */);
+int qvz_layout_ids_from_lines(qvz_gpu *h, const uint8_t *ids_dev);
+int qvz_layout_words_to_lines(qvz_gpu *h, const uint32_t *Yw, uint8_t *out_dev, uint32_t out_stride,
+                              int add_newline);
+int qvz_layout_doubles_to_lines(qvz_gpu *h, const double *Ep, double *out_dev);
+
+// kmeans.cu
+int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev);
+int qvz_kmeans_launch_update(qvz_gpu *h, const int64_t *sums_dev);
+
+// cond_counts.cu
+int qvz_cond_counts_launch(qvz_gpu *h, uint32_t *counts_dev);
+
+// well.cu
+int qvz_well_init(qvz_gpu *h);
+void qvz_well_free(qvz_gpu *h);
+int qvz_well_run_states(qvz_gpu *h, const uint32_t seed[32]);          // fills h->run_states
+int qvz_well_jump_state(qvz_gpu *h, const uint32_t seed[32], uint64_t words, uint32_t *state_dev);
+
+// quantize.cu
+int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err);

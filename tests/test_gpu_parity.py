@@ -1,0 +1,156 @@
+"""CUDA path (through the C ABI of include/qvz_gpu.h) against the oracle, the golden fixtures and the
+compiled reference.  Bit-exact everywhere: integer/byte/index work, and the per-line distortion doubles
+(same additions in the same order)."""
+import numpy as np
+import pytest
+
+from oracle.bindings import DEBUG_SEED, kmeans_init_lines, ref_available
+from qvz_b200.synth import synth_rows
+from tests.helpers import synthetic_tables
+
+pytestmark = pytest.mark.gpu
+
+GLIBC_RAND = [1804289383, 846930886, 1681692777, 1714636915, 1957747793, 424238335, 719885386, 1649760492,
+              596516649, 1189641421, 1025202362, 1350490027, 783368690, 1102520059, 2044897763, 1967513926]
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from qvz_b200 import lib
+    h = lib.Handle(0)
+    yield h
+    h.close()
+
+
+def _load(gpu, rows, c):
+    gpu.load_rows(rows, rows.shape[0], c, rows.shape[1])
+
+
+def test_golden_all_stages(gpu, golden):
+    g = golden
+    c, K = g["columns"], g["clusters"]
+    _load(gpu, g["rows"], c)
+    init = g["rows"][g["picks"].astype(np.int64), :c]
+    r = gpu.kmeans(init, float(g["threshold"]))
+    assert r["iters"] == int(g["iters"])
+    assert np.array_equal(r["ids"], g["ids"])
+    assert np.array_equal(r["means"], g["means"])
+    assert np.array_equal(r["counts"], g["kcounts"])
+    assert np.array_equal(r["moved"], g["moved"])
+    assert np.array_equal(gpu.cond_counts(), g["cond_counts"])
+    q = gpu.quantize(g["tables"], DEBUG_SEED, want_qv=True, want_err=True)
+    assert np.array_equal(q["symbols"], g["symbols"])
+    assert np.array_equal(q["qv"], g["qv"])                       # the -u image, byte for byte
+    assert np.array_equal(q["line_err"], g["line_err"])           # bit-exact doubles
+    assert q["line_err"].sum() / g["rows"].shape[0] == pytest.approx(float(g["distortion"]), rel=1e-12)
+
+
+@pytest.mark.parametrize("words", [0, 1, 31, 32, 33, 1000, 1_000_000, 123_456_789])
+def test_well_jump(gpu, oracle, words):
+    seed = np.random.default_rng(words).integers(0, 2**32, 32, dtype=np.uint32)
+    assert np.array_equal(gpu.well_jump(seed, words), oracle.well_state_after(seed, words))
+
+
+def test_well_jump_known_answer(gpu):
+    assert int(gpu.well_jump(DEBUG_SEED, 1_000_000)[0]) == 0x90e10060
+    # 64-bit offsets: A^(a+b) = A^a A^b
+    a, b = 7_500_000_000, 29_999_999_999
+    assert np.array_equal(gpu.well_jump(gpu.well_jump(DEBUG_SEED, a), b), gpu.well_jump(DEBUG_SEED, a + b))
+
+
+@pytest.mark.parametrize("n,c,k,thr", [(200_000, 150, 3, 4.0), (50_000, 100, 1, 4.0), (30_001, 37, 5, 0.0),
+                                       (4099, 250, 2, 4.0), (999, 5, 8, 4.0), (2000, 9, 11, 4.0),
+                                       (1, 7, 1, 4.0), (5, 1, 1, 4.0), (300, 1022, 2, 4.0)])
+def test_kmeans_and_counts_vs_oracle(gpu, oracle, n, c, k, thr):
+    rows = synth_rows(n, c, seed=1000 + n + c).numpy()
+    picks = kmeans_init_lines(n, k, GLIBC_RAND)
+    if len(set(picks)) < k:                       # tiny inputs: make the initial rows distinct
+        picks = list(range(k))
+    init = rows[picks, :c]
+    o = oracle.kmeans(rows, c, init, thr)
+    _load(gpu, rows, c)
+    if o["iters"] < 0:
+        from qvz_b200.lib import QvzError
+        with pytest.raises(QvzError):
+            gpu.kmeans(init, thr)
+        return
+    r = gpu.kmeans(init, thr)
+    assert r["iters"] == o["iters"]
+    for key in ("ids", "means", "counts", "moved"):
+        assert np.array_equal(r[key], o[key]), key
+    assert np.array_equal(gpu.cond_counts(), oracle.cond_counts(rows, c, k, o["ids"]))
+
+
+@pytest.mark.parametrize("n,c,k,dist", [(60_000, 150, 3, "L"), (20_000, 101, 1, "M"), (7777, 250, 5, "A"), (6, 3, 2, "L")])
+def test_quantize_vs_oracle_synthetic_tables(gpu, oracle, n, c, k, dist):
+    rows = synth_rows(n, c, seed=2000 + n).numpy()
+    ids = np.random.default_rng(n).integers(0, k, n, dtype=np.uint8)
+    t = synthetic_tables(k, c, seed=n, dist=dist)
+    seed = np.random.default_rng(c).integers(0, 2**31, 32, dtype=np.uint32)
+    _load(gpu, rows, c)
+    gpu.set_clusters(k, ids)
+    q = gpu.quantize(t, seed, want_qv=True, want_err=True)
+    o = oracle.quantize(rows, c, ids, t, seed)
+    assert np.array_equal(q["symbols"], o["symbols"])
+    assert np.array_equal(q["qv"], o["qv"])
+    assert np.array_equal(q["line_err"], o["line_err"])
+
+
+def test_quantize_shard_offset(gpu, oracle):
+    # a shard whose first line is L0 continues the draw stream at draw L0*C (multi-GPU contract)
+    n, c, k, L0 = 30_000, 150, 2, 12_344
+    rows = synth_rows(n, c, seed=5).numpy()
+    ids = np.random.default_rng(1).integers(0, k, n, dtype=np.uint8)
+    t = synthetic_tables(k, c, seed=9)
+    whole = oracle.quantize(rows, c, ids, t, DEBUG_SEED)
+    tail = np.ascontiguousarray(rows[L0:])
+    gpu.load_rows(tail, n - L0, c, c + 1, first_line=L0)
+    gpu.set_clusters(k, ids[L0:])
+    q = gpu.quantize(t, DEBUG_SEED, want_qv=True, want_err=True)
+    assert np.array_equal(q["symbols"], whole["symbols"][L0:])
+    assert np.array_equal(q["qv"], whole["qv"][L0:])
+    assert np.array_equal(q["line_err"], whole["line_err"][L0:])
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
+def test_against_compiled_reference(gpu, ref):
+    # the unmodified reference functions (do_kmeans_clustering loop, calculate_statistics, generate_codebooks,
+    # choose_quantizer walk) on the same seeded input, C small so codebook design takes seconds
+    n, c, k = 40_000, 24, 3
+    rows = synth_rows(n, c, seed=31).numpy()
+    picks = kmeans_init_lines(n, k, ref.rand_stream(2 * k))
+    s = ref.session(rows, c, k, threshold=4.0, ratio=0.7)
+    km = s.kmeans(picks)
+    _load(gpu, rows, c)
+    r = gpu.kmeans(rows[picks, :c], 4.0)
+    assert r["iters"] == km["iters"] and np.array_equal(r["ids"], km["ids"]) and np.array_equal(r["means"], km["means"])
+    counts, _ = s.stats()
+    assert np.array_equal(gpu.cond_counts(), counts)
+    t = s.tables()
+    rq = s.quantize(DEBUG_SEED)
+    q = gpu.quantize(t, DEBUG_SEED, want_qv=True, want_err=True)
+    assert np.array_equal(q["symbols"], rq["symbols"])
+    assert np.array_equal(q["qv"], rq["qv"])
+    assert np.array_equal(q["line_err"], rq["line_err"])
+
+
+def test_error_paths(gpu):
+    from qvz_b200.lib import QvzError
+    rows = synth_rows(64, 8, seed=1).numpy()
+    bad = rows.copy()
+    bad[5, 3] = 33 + 72                           # out of the 72-symbol alphabet
+    with pytest.raises(QvzError) as e:
+        gpu.load_rows(bad, 64, 8, 9)
+    assert e.value.code == 4
+    _load(gpu, rows, 8)
+    with pytest.raises(QvzError) as e:            # identical initial centroids -> empty cluster (reference: SIGFPE)
+        gpu.kmeans(np.stack([rows[0, :8], rows[0, :8]]), 4.0)
+    assert e.value.code == 3
+    gpu.set_clusters(1, np.zeros(64, np.uint8))
+    t = synthetic_tables(1, 8, seed=3)
+    t.ctx_of[8 * 72 * 0 + 72 * 3: 72 * 4] = 0xFF   # column 3 loses all its contexts (reference: assert)
+    with pytest.raises(QvzError) as e:
+        gpu.quantize(t, DEBUG_SEED)
+    assert e.value.code == 5
+    with pytest.raises(QvzError):                 # shards must start on a WELL word boundary
+        gpu.load_rows(rows, 64, 8, 9, first_line=2)
