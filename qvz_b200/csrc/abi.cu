@@ -84,7 +84,8 @@ extern "C" void qvz_gpu_close(qvz_gpu *h) {
 	release_rows(h);
 	release_kmeans(h);
 	qvz_well_free(h);
-	free_dev(h->U);
+	free_dev(h->W);
+	free_dev(h->flat);
 	free_dev(h->R);
 	free_dev(h->D);
 	free_dev(h->flags);
@@ -328,49 +329,55 @@ extern "C" int qvz_gpu_cond_counts(qvz_gpu *h, uint32_t *counts_out) {
 }
 
 // ------------------------------------------------------------------------------------------ quantize
-// Compose ctx_of -> (qmap, smap) into U / R (see quantize.cu) on the host and upload.
-static int upload_tables(qvz_gpu *h, const struct qvz_flat_tables *t) {
+// Upload the caller's flat tables and compose W / R (see quantize.cu) on the device.
+static int upload_tables(qvz_gpu *h, const struct qvz_flat_tables *t, int *toeplitz) {
 	const uint32_t K = t->clusters, C = t->columns;
-	const size_t rows = (size_t) K * C * 72;
-	const size_t u_elems = rows * 2 * 72;
-	std::vector<uint16_t> U(u_elems, 0);
-	std::vector<uint8_t> R(rows, 0xFF);
-	for (size_t kc = 0; kc < (size_t) K * C; ++kc) {
-		if (t->nctx[kc] > 72 || (t->q_off[kc] & 1)) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: malformed flat tables");
-		for (uint32_t v = 0; v < 72; ++v) {
-			const uint32_t ctx = t->ctx_of[kc * 72 + v];
-			if (ctx == QVZ_CTX_ABSENT) continue;
-			if (ctx >= t->nctx[kc]) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: context index out of range");
-			R[kc * 72 + v] = t->qratio[t->q_off[kc] / 2 + ctx];
-			for (uint32_t hi = 0; hi < 2; ++hi) {
-				const uint8_t *qm = t->qmap + (t->q_off[kc] + 2 * ctx + hi) * 72;
-				const uint8_t *sm = t->smap + (t->q_off[kc] + 2 * ctx + hi) * 72;
-				uint16_t *dst = &U[((kc * 72 + v) * 2 + hi) * 72];
-				for (uint32_t x = 0; x < 72; ++x) {
-					const uint32_t qv = qm[x];
-					if (qv >= 72) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: quantized value out of range");
-					dst[x] = (uint16_t) ((sm[qv] & 0x7F) | (qv << 8));
-				}
-			}
-		}
+	const size_t KC = (size_t) K * C;
+	const uint64_t nq = t->q_off[KC - 1] + 2ull * t->nctx[KC - 1];
+	// device staging layout (all offsets 8-byte aligned)
+	const size_t o_qoff = 0, o_nctx = o_qoff + KC * 8, o_ctx = (o_nctx + KC * 4 + 7) & ~(size_t) 7;
+	const size_t o_ratio = (o_ctx + KC * 72 + 7) & ~(size_t) 7, o_qmap = (o_ratio + nq / 2 + 7) & ~(size_t) 7;
+	const size_t o_smap = (o_qmap + nq * 72 + 7) & ~(size_t) 7, total = o_smap + nq * 72;
+	if (h->flat_cap < total) {
+		free_dev(h->flat);
+		h->flat = nullptr;
+		QVZ_CUDA(h, cudaMalloc(&h->flat, total));
+		h->flat_cap = total;
 	}
-	if (h->U_cap < u_elems * sizeof(uint16_t)) {
-		free_dev(h->U);
-		h->U = nullptr;
-		QVZ_CUDA(h, cudaMalloc(&h->U, u_elems * sizeof(uint16_t)));
-		h->U_cap = u_elems * sizeof(uint16_t);
+	const size_t w_bytes = KC * 72 * 72 * sizeof(uint32_t), r_bytes = KC * 72;
+	if (h->W_cap < w_bytes) {
+		free_dev(h->W);
+		h->W = nullptr;
+		QVZ_CUDA(h, cudaMalloc(&h->W, w_bytes));
+		h->W_cap = w_bytes;
 	}
-	if (h->R_cap < rows) {
+	if (h->R_cap < r_bytes) {
 		free_dev(h->R);
 		h->R = nullptr;
-		QVZ_CUDA(h, cudaMalloc(&h->R, rows));
-		h->R_cap = rows;
+		QVZ_CUDA(h, cudaMalloc(&h->R, r_bytes));
+		h->R_cap = r_bytes;
 	}
-	QVZ_CUDA(h, cudaMemcpyAsync(h->U, U.data(), u_elems * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
-	QVZ_CUDA(h, cudaMemcpyAsync(h->R, R.data(), rows, cudaMemcpyHostToDevice, h->stream));
-	QVZ_CUDA(h, cudaMemcpyAsync(h->D, t->distortion, 72 * 72 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));       // U/R are function-local host buffers
-	return QVZ_OK;
+	const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
+	QVZ_CUDA(h, cudaMemcpyAsync(h->flat + o_qoff, t->q_off, KC * 8, H2D, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->flat + o_nctx, t->nctx, KC * 4, H2D, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->flat + o_ctx, t->ctx_of, KC * 72, H2D, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->flat + o_ratio, t->qratio, nq / 2, H2D, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->flat + o_qmap, t->qmap, nq * 72, H2D, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->flat + o_smap, t->smap, nq * 72, H2D, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->D, t->distortion, 72 * 72 * sizeof(double), H2D, h->stream));
+	// is the distortion a function of |x - y| only (true for -d M / L / A; a custom -D matrix may not be)?
+	*toeplitz = 1;
+	for (uint32_t y = 0; y < 72 && *toeplitz; ++y)
+		for (uint32_t x = 0; x < 72; ++x) {
+			const uint32_t d = x > y ? x - y : y - x;
+			if (memcmp(&t->distortion[x + 72 * y], &t->distortion[d], sizeof(double)) != 0) {
+				*toeplitz = 0;
+				break;
+			}
+		}
+	return qvz_quantize_compose(h, (uint32_t) KC, (const uint32_t *) (h->flat + o_nctx), h->flat + o_ctx,
+	                            (const uint64_t *) (h->flat + o_qoff), h->flat + o_ratio, h->flat + o_qmap,
+	                            h->flat + o_smap);
 }
 
 extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, const uint32_t well_seed[32],
@@ -389,12 +396,13 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	if (!h->run_states) QVZ_CUDA(h, cudaMalloc(&h->run_states, (size_t) L.T * 32 * sizeof(uint32_t)));
 
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
-	int rc = upload_tables(h, t);
+	int toeplitz = 0;
+	int rc = upload_tables(h, t, &toeplitz);
 	if (rc) return rc;
 	rc = qvz_well_run_states(h, well_seed);
 	if (rc) return rc;
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
-	rc = qvz_quantize_launch(h, qv_out != nullptr, line_err_out != nullptr);
+	rc = qvz_quantize_launch(h, qv_out != nullptr, line_err_out != nullptr, toeplitz);
 	if (rc) return rc;
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));
 
@@ -429,9 +437,12 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	if (rc) return rc;
 	if (e != cudaSuccess) QVZ_FAIL(h, QVZ_ERR_CUDA, "quantize egress: %s", cudaGetErrorString(e));
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_D], h->stream));
-	int missing = 0;
+	int missing = 0, malformed = 0;
 	rc = take_flag(h, 2, &missing);
 	if (rc) return rc;
+	rc = take_flag(h, 3, &malformed);
+	if (rc) return rc;
+	if (malformed) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: malformed flat tables (context index or quantized value out of range)");
 	h->tm.quantize_setup_ms = ev_ms(h, EV_A, EV_B);
 	h->tm.quantize_ms = ev_ms(h, EV_B, EV_C);
 	h->tm.quantize_d2h_ms = ev_ms(h, EV_C, EV_D);

@@ -15,7 +15,8 @@
 #define QVZ_CC_GROUP 5u                         // clusters per pass: 5 * 4 * 72*72 * 2 B = 207 360 B of shared memory
 #define QVZ_CC_SLICE_WORDS (72u * 72u / 2u)      // 2592 words per (cluster, column) slice
 #define QVZ_CC_CHUNK 65280u                      // slots per CTA (multiple of 256, < 65536)
-#define QVZ_CC_THREADS 512
+#define QVZ_CC_THREADS 1024
+#define QVZ_CC_UNROLL 4
 
 __global__ void __launch_bounds__(QVZ_CC_THREADS)
 qvz_cond_counts_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint8_t *__restrict__ cl,
@@ -33,19 +34,30 @@ qvz_cond_counts_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint
 
 	const uint32_t *xc = Xw + (uint64_t) c4 * L.P;
 	const uint32_t *xp = c4 ? xc - L.P : xc;
-	for (uint64_t p = p0 + threadIdx.x; p < p1; p += QVZ_CC_THREADS) {
-		const uint32_t k = cl[p];
-		const uint32_t g = k - kbase;              // wraps to a huge value for k < kbase and for 0xFF
-		if (g >= G) continue;
-		const uint32_t w = xc[p] - 0x21212121u;    // ingest guarantees every real byte >= 33: no borrow
-		uint32_t prev = c4 ? ((xp[p] >> 24) - 33u) : 0u;
+	for (uint64_t pb = p0 + threadIdx.x; pb < p1; pb += (uint64_t) QVZ_CC_UNROLL * QVZ_CC_THREADS) {
+		uint32_t kk[QVZ_CC_UNROLL], ww[QVZ_CC_UNROLL], pp[QVZ_CC_UNROLL];
 #pragma unroll
-		for (uint32_t j = 0; j < 4; ++j) {
-			if (4 * c4 + j < L.C) {
-				const uint32_t cur = (w >> (8 * j)) & 0xFFu;
-				const uint32_t bin = prev * 72u + cur;
-				atomicAdd(&tab[(g * 4 + j) * QVZ_CC_SLICE_WORDS + (bin >> 1)], 1u << (16 * (bin & 1)));
-				prev = cur;
+		for (int u = 0; u < QVZ_CC_UNROLL; ++u) {    // all loads first: 3*UNROLL independent requests in flight
+			const uint64_t p = pb + (uint64_t) u * QVZ_CC_THREADS;
+			const bool in = p < p1;
+			kk[u] = in ? cl[p] : QVZ_NO_LINE;
+			ww[u] = in ? xc[p] : 0u;
+			pp[u] = (in && c4) ? xp[p] : 0x21212121u;
+		}
+#pragma unroll
+		for (int u = 0; u < QVZ_CC_UNROLL; ++u) {
+			const uint32_t g = kk[u] - kbase;        // wraps to a huge value for k < kbase and for 0xFF
+			if (g >= G) continue;
+			const uint32_t w = ww[u] - 0x21212121u;  // ingest guarantees every real byte >= 33: no borrow
+			uint32_t prev = c4 ? ((pp[u] >> 24) - 33u) : 0u;
+#pragma unroll
+			for (uint32_t j = 0; j < 4; ++j) {
+				if (4 * c4 + j < L.C) {
+					const uint32_t cur = (w >> (8 * j)) & 0xFFu;
+					const uint32_t bin = prev * 72u + cur;
+					atomicAdd(&tab[(g * 4 + j) * QVZ_CC_SLICE_WORDS + (bin >> 1)], 1u << (16 * (bin & 1)));
+					prev = cur;
+				}
 			}
 		}
 	}

@@ -9,12 +9,21 @@
 //              argmin_k sum (x-m_k)^2  =  argmin_k ( sum m_k^2  -  2 * sum x*m_k )   (sum x^2 is common),
 //              and sum x*m_k over 4 columns is one dp4a on the packed words.  Ties: strict '<' in
 //              cluster order => lowest id wins, as in assign_cluster.
-//   sums:      accumulator[cluster][col] += byte  (uint64 in the reference) -> warp REDUX of the packed
-//              16-bit fields per (cluster, word), CTA-level uint32 partials in shared memory, one
-//              64-bit global atomic per (cluster, column, CTA).  Integer sums are order independent.
+//   sums:      accumulator[cluster][col] += byte  (uint64 in the reference) -> the tile's rows are counting-
+//              sorted by cluster in shared memory and summed column-word-wise as packed 16-bit halves,
+//              CTA-level uint32 partials in shared memory, one 64-bit global atomic per (cluster, column,
+//              CTA).  Integer sums are order independent.
 //   recenter:  mean = (uint8)(sum / count), moved_k = sum (new-old)^2 -- tiny second kernel.
 #include "qvz_internal.cuh"
 
+// Shared-memory plan of one CTA (R = blockDim.x rows per tile):
+//   mean_s[K][C4]  msq[K]  cnt[K]  acc[K][C4*4]  off[(NW+1)*K + 1]  perm[R] (u16)  tile[C4][R+1]
+// Per tile of R slots:
+//   phase 1  thread <-> row: load the row's packed words (coalesced across the warp), park them in
+//            tile[c4][row] (pitch R+1: conflict free both ways), K dp4a per word, argmin;
+//   sort     counting sort of the tile's rows by cluster (ballot/popc ranks + a tiny scan) -> perm[];
+//   phase 2  thread <-> (column word, part): walks the cluster-contiguous row lists, adding the packed
+//            16-bit halves (<= 256 rows x 255 < 2^16), one 4-way unpack + shared atomic per (cluster, word).
 template <int KT>
 __global__ void __launch_bounds__(QVZ_THREADS)
 qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t *__restrict__ cl,
@@ -22,77 +31,120 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
                          uint32_t Krt, unsigned long long *__restrict__ sums)
 {
 	const uint32_t K = KT > 0 ? (uint32_t) KT : Krt;
-	const uint32_t C4 = L.C4;
+	const uint32_t C4 = L.C4, R = blockDim.x, NW = R >> 5, pitch = R + 1;
 	extern __shared__ uint32_t sm[];
 	uint32_t *mean_s = sm;                       // [K][C4]
-	uint32_t *acc = mean_s + K * C4;             // [K][C4*4]
-	uint32_t *cnt = acc + K * C4 * 4;            // [K]
-	uint32_t *msq = cnt + K;                     // [K]
+	uint32_t *msq = mean_s + K * C4;             // [K]
+	uint32_t *cnt = msq + K;                     // [K]
+	uint32_t *acc = cnt + K;                     // [K][C4*4]
+	uint32_t *off = acc + K * C4 * 4;            // [(NW+1)][K] exclusive offsets, then [K] totals scratch
+	uint16_t *perm = (uint16_t *) (off + (NW + 1) * K + 1);
+	uint32_t *tile = (uint32_t *) (perm + R + (R & 1));
 
-	for (uint32_t i = threadIdx.x; i < K * C4; i += QVZ_THREADS) mean_s[i] = means_w[i];
-	for (uint32_t i = threadIdx.x; i < K * C4 * 4; i += QVZ_THREADS) acc[i] = 0;
-	if (threadIdx.x < K) {
-		cnt[threadIdx.x] = 0;
-		msq[threadIdx.x] = means_sq[threadIdx.x];
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	for (uint32_t i = tid; i < K * C4; i += R) mean_s[i] = means_w[i];
+	for (uint32_t i = tid; i < K * C4 * 4; i += R) acc[i] = 0;
+	if (tid < K) {
+		cnt[tid] = 0;
+		msq[tid] = means_sq[tid];
 	}
 	__syncthreads();
 
-	const uint32_t lane = threadIdx.x & 31;
-	for (uint64_t base = (uint64_t) blockIdx.x * QVZ_THREADS; base < L.P; base += (uint64_t) gridDim.x * QVZ_THREADS) {
-		const uint64_t p = base + threadIdx.x;       // P is a multiple of QVZ_THREADS: whole warps stay active
+	const uint32_t nparts = (R / C4) ? (R / C4) : 1;
+	for (uint64_t base = (uint64_t) blockIdx.x * R; base < L.P; base += (uint64_t) gridDim.x * R) {
+		const uint64_t p = base + tid;               // P is a multiple of 256 and of R
 		const bool valid = cl[p] != QVZ_NO_LINE;
 		uint32_t best = 0;
-		if (K > 1) {
+		{
 			uint32_t D[KT > 0 ? KT : QVZ_MAX_K];
 #pragma unroll
 			for (int k = 0; k < (KT > 0 ? KT : QVZ_MAX_K); ++k) D[k] = 0;
+			const uint32_t *xp = Xw + p;
+			uint32_t *tp = tile + tid;
+#pragma unroll 4
 			for (uint32_t c4 = 0; c4 < C4; ++c4) {
-				const uint32_t w = Xw[(uint64_t) c4 * L.P + p];
+				const uint32_t w = xp[(uint64_t) c4 * L.P];
+				tp[c4 * pitch] = w;
+				if (KT != 1) {
 #pragma unroll
-				for (int k = 0; k < (KT > 0 ? KT : QVZ_MAX_K); ++k)
-					if (KT > 0 || (uint32_t) k < K) D[k] = __dp4a(w, mean_s[k * C4 + c4], D[k]);
+					for (int k = 0; k < (KT > 0 ? KT : QVZ_MAX_K); ++k)
+						if (KT > 0 || (uint32_t) k < K) D[k] = __dp4a(w, mean_s[k * C4 + c4], D[k]);
+				}
 			}
-			int bestv = (int) msq[0] - 2 * (int) D[0];
+			if (KT != 1) {
+				int bestv = (int) msq[0] - 2 * (int) D[0];
 #pragma unroll
-			for (int k = 1; k < (KT > 0 ? KT : QVZ_MAX_K); ++k) {
-				if (KT > 0 || (uint32_t) k < K) {
-					const int v = (int) msq[k] - 2 * (int) D[k];
-					if (v < bestv) {
-						bestv = v;
-						best = k;
+				for (int k = 1; k < (KT > 0 ? KT : QVZ_MAX_K); ++k) {
+					if (KT > 0 || (uint32_t) k < K) {
+						const int v = (int) msq[k] - 2 * (int) D[k];
+						if (v < bestv) {             // strict '<': lowest cluster id wins ties (assign_cluster)
+							bestv = v;
+							best = k;
+						}
 					}
 				}
 			}
 		}
 		if (valid) cl[p] = (uint8_t) best;
+		const uint32_t key = valid ? best : 0;       // empty slots hold zero words: harmless in any list
 
-		// column sums of this warp's 32 rows, per cluster (slots without a line hold zero words)
-		for (uint32_t c4 = 0; c4 < C4; ++c4) {
-			const uint32_t w = Xw[(uint64_t) c4 * L.P + p];
-			const uint32_t lo = w & 0x00FF00FFu, hi = (w >> 8) & 0x00FF00FFu;
+		// counting sort by cluster
+		uint32_t rank = 0;
+		for (uint32_t k = 0; k < K; ++k) {
+			const uint32_t m = __ballot_sync(0xFFFFFFFFu, key == k);
+			if (key == k) rank = __popc(m & ((1u << lane) - 1));
+			if (lane == 0) off[(warp + 1) * K + k] = __popc(m);
+			const uint32_t nv = __popc(__ballot_sync(0xFFFFFFFFu, valid && best == k));
+			if (lane == 0 && nv) atomicAdd(&cnt[k], nv);
+		}
+		__syncthreads();
+		if (tid < K) {                               // column k: running sum over warps, totals in the last row
+			uint32_t run = 0;
+			for (uint32_t w = 0; w < NW; ++w) {
+				const uint32_t c = off[(w + 1) * K + tid];
+				off[w * K + tid] = run;
+				run += c;
+			}
+			off[NW * K + tid] = run;
+		}
+		__syncthreads();
+		{
+			uint32_t start = 0;
+			for (uint32_t k = 0; k < key; ++k) start += off[NW * K + k];
+			perm[start + off[warp * K + key] + rank] = (uint16_t) tid;
+		}
+		__syncthreads();
+
+		// column sums over the cluster-contiguous lists
+		for (uint32_t item = tid; item < C4 * nparts; item += R) {
+			const uint32_t c4 = item % C4, part = item / C4;
+			const uint32_t *tc = tile + c4 * pitch;
+			uint32_t seg = 0;
 			for (uint32_t k = 0; k < K; ++k) {
-				const bool mine = (K == 1) || (best == k);
-				const uint32_t slo = __reduce_add_sync(0xFFFFFFFFu, mine ? lo : 0u);
-				const uint32_t shi = __reduce_add_sync(0xFFFFFFFFu, mine ? hi : 0u);
-				if (lane < 4) {
-					const uint32_t pair = (lane & 1) ? shi : slo;            // bytes 1,3 live in hi; 0,2 in lo
-					const uint32_t f = (lane & 2) ? (pair >> 16) : (pair & 0xFFFFu);
-					if (f) atomicAdd(&acc[(k * C4 + c4) * 4 + lane], f);
+				const uint32_t end = seg + off[NW * K + k];
+				uint32_t lo = 0, hi = 0;
+				for (uint32_t j = seg + part; j < end; j += nparts) {
+					const uint32_t w = tc[perm[j]];
+					lo += w & 0x00FF00FFu;
+					hi += (w >> 8) & 0x00FF00FFu;
 				}
+				if (lo | hi) {
+					uint32_t *a = acc + (k * C4 + c4) * 4;
+					atomicAdd(a + 0, lo & 0xFFFFu);
+					atomicAdd(a + 1, hi & 0xFFFFu);
+					atomicAdd(a + 2, lo >> 16);
+					atomicAdd(a + 3, hi >> 16);
+				}
+				seg = end;
 			}
 		}
-		for (uint32_t k = 0; k < K; ++k) {
-			const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, valid && best == k));
-			if (lane == 0 && n) atomicAdd(&cnt[k], n);
-		}
+		__syncthreads();
 	}
-	__syncthreads();
-	for (uint32_t i = threadIdx.x; i < K * C4 * 4; i += QVZ_THREADS) {
+	for (uint32_t i = tid; i < K * C4 * 4; i += R) {
 		const uint32_t k = i / (C4 * 4), c = i - k * C4 * 4;
 		if (c < L.C && acc[i]) atomicAdd(&sums[(uint64_t) k * L.C + c], (unsigned long long) acc[i]);
 	}
-	if (threadIdx.x < K && cnt[threadIdx.x])
-		atomicAdd(&sums[(uint64_t) K * L.C + threadIdx.x], (unsigned long long) cnt[threadIdx.x]);
+	if (tid < K && cnt[tid]) atomicAdd(&sums[(uint64_t) K * L.C + tid], (unsigned long long) cnt[tid]);
 }
 
 // recalculate_means (src/cluster.c:106-128) on the reduced sums; also repacks the centroids for dp4a.
@@ -152,32 +204,42 @@ qvz_kmeans_update_kernel(uint32_t K, uint32_t C, uint32_t C4, const unsigned lon
 	}
 }
 
+static size_t assign_smem(uint32_t K, uint32_t C4, uint32_t R) {
+	const uint32_t NW = R / 32;
+	size_t words = (size_t) K * C4 + 2 * K + (size_t) K * C4 * 4 + (NW + 1) * K + 1;
+	words += (R + (R & 1)) / 2 + (size_t) C4 * (R + 1);
+	return words * sizeof(uint32_t);
+}
+
 template <int KT>
-static void launch_assign(qvz_gpu *h, int64_t *sums_dev, unsigned grid, size_t smem) {
+static void launch_assign(qvz_gpu *h, int64_t *sums_dev, unsigned grid, unsigned R, size_t smem) {
 	auto kern = qvz_kmeans_assign_kernel<KT>;
-	if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-	kern<<<grid, QVZ_THREADS, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K,
-	                                             (unsigned long long *) sums_dev);
+	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	kern<<<grid, R, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K,
+	                                   (unsigned long long *) sums_dev);
 }
 
 int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev) {
 	const uint32_t K = h->km_K, C4 = h->L.C4;
-	const size_t smem = ((size_t) K * C4 * 5 + 2 * K) * sizeof(uint32_t);
-	if (smem > 200 * 1024) QVZ_FAIL(h, QVZ_ERR_UNSUPPORTED, "k-means: K*columns too large for shared memory");
-	uint64_t blocks = h->L.P / QVZ_THREADS;
-	const uint64_t cap = (uint64_t) h->sm_count * 8;
+	unsigned R = 256;
+	while (R > 32 && assign_smem(K, C4, R) > 110 * 1024) R >>= 1;       // keep >= 2 CTAs per SM when possible
+	const size_t smem = assign_smem(K, C4, R);
+	if (smem > 220 * 1024) QVZ_FAIL(h, QVZ_ERR_UNSUPPORTED, "k-means: K*columns too large for shared memory");
+	const uint64_t blocks = h->L.P / R;
+	const uint64_t per_sm = (220 * 1024) / smem < (2048 / R) ? (220 * 1024) / smem : (2048 / R);
+	const uint64_t cap = (uint64_t) h->sm_count * (per_sm ? per_sm : 1);
 	const unsigned grid = (unsigned) (blocks < cap ? blocks : cap);
 	QVZ_CUDA(h, cudaMemsetAsync(sums_dev, 0, ((size_t) K * h->L.C + K) * sizeof(int64_t), h->stream));
 	switch (K) {
-	case 1: launch_assign<1>(h, sums_dev, grid, smem); break;
-	case 2: launch_assign<2>(h, sums_dev, grid, smem); break;
-	case 3: launch_assign<3>(h, sums_dev, grid, smem); break;
-	case 4: launch_assign<4>(h, sums_dev, grid, smem); break;
-	case 5: launch_assign<5>(h, sums_dev, grid, smem); break;
-	case 6: launch_assign<6>(h, sums_dev, grid, smem); break;
-	case 7: launch_assign<7>(h, sums_dev, grid, smem); break;
-	case 8: launch_assign<8>(h, sums_dev, grid, smem); break;
-	default: launch_assign<0>(h, sums_dev, grid, smem); break;
+	case 1: launch_assign<1>(h, sums_dev, grid, R, smem); break;
+	case 2: launch_assign<2>(h, sums_dev, grid, R, smem); break;
+	case 3: launch_assign<3>(h, sums_dev, grid, R, smem); break;
+	case 4: launch_assign<4>(h, sums_dev, grid, R, smem); break;
+	case 5: launch_assign<5>(h, sums_dev, grid, R, smem); break;
+	case 6: launch_assign<6>(h, sums_dev, grid, R, smem); break;
+	case 7: launch_assign<7>(h, sums_dev, grid, R, smem); break;
+	case 8: launch_assign<8>(h, sums_dev, grid, R, smem); break;
+	default: launch_assign<0>(h, sums_dev, grid, R, smem); break;
 	}
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());

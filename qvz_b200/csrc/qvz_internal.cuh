@@ -64,10 +64,12 @@ struct qvz_gpu {
 	uint32_t *h_counts;      // pinned [K]
 
 	// quantize state
-	uint16_t *U;             // [K][C][72 prev][2 hi][72 data] -> state | qv << 8
+	uint32_t *W;             // [K][C][72 prev][72 data] -> qv_lo | qv_hi<<8 | state_lo<<16 | state_hi<<24
 	uint8_t *R;              // [K][C][72 prev] qratio, 0xFF = no such context
 	double *D;               // [72*72]
-	size_t U_cap, R_cap;
+	size_t W_cap, R_cap;
+	uint8_t *flat;           // staging copy of the caller's flat tables
+	size_t flat_cap;
 	uint32_t *run_states;    // [T][32] WELL state (n = 0 frame) at the first draw of each run
 	uint32_t *Yw, *Qw;       // [C4][P] packed outputs (state|hi<<7, qv+33)
 	double *Ep;              // [P] per-slot error / C
@@ -118,4 +120,6 @@ int qvz_well_run_states(qvz_gpu *h, const uint32_t seed[32]);          // fills 
 int qvz_well_jump_state(qvz_gpu *h, const uint32_t seed[32], uint64_t words, uint32_t *state_dev);
 
 // quantize.cu
-int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err);
+int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int toeplitz);
+int qvz_quantize_compose(qvz_gpu *h, uint32_t KC, const uint32_t *nctx, const uint8_t *ctx_of, const uint64_t *q_off,
+                         const uint8_t *qratio, const uint8_t *qmap, const uint8_t *smap);
