@@ -365,7 +365,8 @@ static int upload_tables(qvz_gpu *h, const struct qvz_flat_tables *t, int *toepl
 	QVZ_CUDA(h, cudaMemcpyAsync(h->flat + o_qmap, t->qmap, nq * 72, H2D, h->stream));
 	QVZ_CUDA(h, cudaMemcpyAsync(h->flat + o_smap, t->smap, nq * 72, H2D, h->stream));
 	QVZ_CUDA(h, cudaMemcpyAsync(h->D, t->distortion, 72 * 72 * sizeof(double), H2D, h->stream));
-	// is the distortion a function of |x - y| only (true for -d M / L / A; a custom -D matrix may not be)?
+	// distortion mode: 1 = a function of |x - y| only (true for -d M / L / A; a custom -D matrix may not be),
+	// 2 = additionally integer-valued and small enough that a line's sum fits uint32 (-d M, -d A)
 	*toeplitz = 1;
 	for (uint32_t y = 0; y < 72 && *toeplitz; ++y)
 		for (uint32_t x = 0; x < 72; ++x) {
@@ -375,6 +376,14 @@ static int upload_tables(qvz_gpu *h, const struct qvz_flat_tables *t, int *toepl
 				break;
 			}
 		}
+	if (*toeplitz) {
+		bool integral = true;
+		for (uint32_t d = 0; d < 72; ++d) {
+			const double f = t->distortion[d];
+			if (!(f >= 0.0 && f <= 2097152.0 && f == floor(f))) integral = false;     // 1022 columns * 2^21 < 2^32
+		}
+		if (integral) *toeplitz = 2;
+	}
 	return qvz_quantize_compose(h, (uint32_t) KC, (const uint32_t *) (h->flat + o_nctx), h->flat + o_ctx,
 	                            (const uint64_t *) (h->flat + o_qoff), h->flat + o_ratio, h->flat + o_qmap,
 	                            h->flat + o_smap);
@@ -392,7 +401,7 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	const size_t wbytes = (size_t) L.C4 * L.P * sizeof(uint32_t);
 	if (!h->Yw) QVZ_CUDA(h, cudaMalloc(&h->Yw, wbytes));
 	if (qv_out && !h->Qw) QVZ_CUDA(h, cudaMalloc(&h->Qw, wbytes));
-	if (line_err_out && !h->Ep) QVZ_CUDA(h, cudaMalloc(&h->Ep, (size_t) L.P * sizeof(double)));
+	if (!h->Ep) QVZ_CUDA(h, cudaMalloc(&h->Ep, (size_t) L.P * sizeof(double)));   // the walk always sums the distortion, like the reference
 	if (!h->run_states) QVZ_CUDA(h, cudaMalloc(&h->run_states, (size_t) L.T * 32 * sizeof(uint32_t)));
 
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
@@ -402,7 +411,7 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	rc = qvz_well_run_states(h, well_seed);
 	if (rc) return rc;
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
-	rc = qvz_quantize_launch(h, qv_out != nullptr, line_err_out != nullptr, toeplitz);
+	rc = qvz_quantize_launch(h, qv_out != nullptr, 1, toeplitz);
 	if (rc) return rc;
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));
 

@@ -9,23 +9,34 @@
 // (state, hi) stream -- legal because the coder never feeds back into the quantizer choice.
 //
 // One thread walks one run of Lr consecutive lines, so its draws are one contiguous piece of the
-// reference's WELL stream: it starts from the jump-ahead state of well.cu and then runs the reference's
-// own bit server (refill when fewer than 7 bits are left).  All threads are at the same column at the
-// same time, adjacent threads hold adjacent slots => packed words are read and written coalesced.
+// reference's WELL stream: it starts from the jump-ahead state of well.cu and serves 4 draws per word,
+// low bits first, exactly like the reference's bit server.  Every run starts on a word boundary, so the
+// refill position inside a line is known statically: line i of a run starts at draw i*C, i.e. at
+// sub-draw PH = (i*C) & 3 of a word, and a full 4-symbol data word refills before symbol (4-PH)&3.
+// All threads are at the same column at the same time, adjacent threads hold adjacent slots => packed
+// words are read and written coalesced.
 //
 // Tables (built by qvz_quantize_compose_kernel from `struct qvz_flat_tables`):
-//   W[k][col][prev_qv][data] = qv_lo | qv_hi << 8 | state_lo << 16 | state_hi << 24
+//   W[k][col][prev_qv][data] = qv_lo | qv_hi << 8 | state_lo << 16 | (state_hi | 0x80) << 24
 //       the composition ctx_of -> (qmap, smap) for BOTH quantizers of the context, indexed by the previous
-//       quantized VALUE: one dependent load per symbol gives both candidates;
+//       quantized VALUE: one dependent load per symbol gives both candidates; the output byte
+//       (state | hi << 7) is byte 2+hi of the entry;
 //   R[k][col][prev_qv]       = qratio, or 0xFF where the reference would hit its assert (codebook.c:164);
 //       loaded in parallel with W (same dependence), the lo/hi choice is a byte select afterwards.
 // The hot part of W per column is a few KB (a band around prev ~ data), so it lives in L1: the kernel
 // asks for a shared-memory carve-out that leaves ~100 KB of L1 and streams the row words past it
 // (ld.global.nc.L1::no_allocate / st.global.L1::no_allocate).
+//
+// Distortion (src/qv_compressor.c:97,118,127): DMODE 2 = the matrix is a function of |x-y| with integer
+// values (-d M, -d A): the per-line sum is accumulated in uint32 (every partial sum of the reference's
+// double additions is the same exact integer); DMODE 1 = function of |x-y| (-d L): doubles from shared
+// memory added in column order (bit-identical to the reference's sequence of additions);
+// DMODE 0 = arbitrary 72x72 matrix (-D file) read from global memory.
 #include "qvz_internal.cuh"
 
 #define QZ_THREADS QVZ_THREADS
 #define QZ_BLOCKS_PER_SM 4
+#define QZ_WS_WORDS (32 * QZ_THREADS)
 
 __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
 	uint32_t v;
@@ -36,7 +47,89 @@ __device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v) {
 	asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v));
 }
 
-template <bool TOEPLITZ>
+struct qz_ctx {
+	const uint32_t *W;
+	const uint8_t *R;
+	const double *D;
+	uint32_t *ws;          // this thread's column of the WELL ring: ws[k * QZ_THREADS]
+	const double *dd;      // shared |x-y| tables
+	const uint32_t *di;
+	uint32_t n10;          // ring index << 10 (bytes: 4 * QZ_THREADS per ring slot), uniform
+	uint32_t bits;         // undrawn part of the current WELL word
+	uint32_t prev, wbase, rbase, maxratio;
+	uint32_t erri;
+	double errd;
+};
+
+// well_1024a (src/well.c:8-24) on the shared-memory ring
+__device__ __forceinline__ void qz_refill(qz_ctx &q) {
+	char *base = (char *) q.ws;
+	const uint32_t n10 = q.n10;
+	const uint32_t z0 = *(uint32_t *) (base + ((n10 + 31u * 1024u) & 0x7C00u));
+	const uint32_t a = *(uint32_t *) (base + ((n10 + 3u * 1024u) & 0x7C00u));
+	const uint32_t b = *(uint32_t *) (base + ((n10 + 24u * 1024u) & 0x7C00u));
+	const uint32_t c = *(uint32_t *) (base + ((n10 + 10u * 1024u) & 0x7C00u));
+	const uint32_t z1 = *(uint32_t *) (base + n10) ^ (a ^ (a >> 8));
+	const uint32_t z2 = (b ^ (b << 19)) ^ (c ^ (c << 14));
+	*(uint32_t *) (base + n10) = z1 ^ z2;
+	q.n10 = (n10 + 31u * 1024u) & 0x7C00u;
+	q.bits = (z0 ^ (z0 << 11)) ^ (z1 ^ (z1 << 7)) ^ (z2 ^ (z2 << 13));
+	*(uint32_t *) (base + q.n10) = q.bits;
+}
+
+// one symbol: byte J of the data word w; returns with outw / qvw byte J filled in
+template <int DMODE, bool WANT_QV, int J>
+__device__ __forceinline__ void qz_symbol(qz_ctx &q, uint32_t w, uint32_t &outw, uint32_t &qvw) {
+	const uint32_t draw = q.bits & 127u;
+	q.bits >>= 7;
+	const uint32_t data = __byte_perm(w, 0, 0x4440 + J);
+	const uint32_t e = __ldg(q.W + (q.wbase + data + q.prev * 72u));
+	const uint32_t ratio = __ldg(q.R + (q.rbase + q.prev));
+	q.maxratio = max(q.maxratio, ratio);
+	const uint32_t hi = draw >= ratio;
+	const uint32_t qv = __byte_perm(e, 0, 0x4440 + hi);                    // byte hi of e
+	// insert byte 2+hi of e (state | hi<<7) at byte J of outw; byte hi of e (qv) at byte J of qvw
+	outw = __byte_perm(outw, e, (0x3210 & ~(0xF << (4 * J))) + ((6 + hi) << (4 * J)));
+	if (WANT_QV) qvw = __byte_perm(qvw, e, (0x3210 & ~(0xF << (4 * J))) + ((4 + hi) << (4 * J)));
+	if (DMODE == 2) {
+		q.erri += q.di[abs((int) data - (int) qv)];
+	} else if (DMODE == 1) {
+		q.errd += q.dd[abs((int) data - (int) qv)];
+	} else {
+		q.errd += __ldg(&q.D[data + 72u * qv]);
+	}
+	q.prev = qv;
+	q.wbase += 72u * 72u;
+	q.rbase += 72u;
+}
+
+// one full data word; PH = sub-draw position of the word's first symbol inside its WELL word
+template <int DMODE, bool WANT_QV, int PH>
+__device__ __forceinline__ void qz_word(qz_ctx &q, uint32_t w, uint32_t &outw, uint32_t &qvw) {
+	if (PH == 0) qz_refill(q);
+	qz_symbol<DMODE, WANT_QV, 0>(q, w, outw, qvw);
+	if (PH == 3) qz_refill(q);
+	qz_symbol<DMODE, WANT_QV, 1>(q, w, outw, qvw);
+	if (PH == 2) qz_refill(q);
+	qz_symbol<DMODE, WANT_QV, 2>(q, w, outw, qvw);
+	if (PH == 1) qz_refill(q);
+	qz_symbol<DMODE, WANT_QV, 3>(q, w, outw, qvw);
+}
+
+template <int DMODE, bool WANT_QV, int PH>
+__device__ __forceinline__ void qz_full_words(qz_ctx &q, const qvz_layout &L, bool valid, const uint32_t *xp,
+                                              uint32_t *yp, uint32_t *qp, uint32_t full, uint32_t &wnext) {
+	for (uint32_t c4 = 0; c4 < full; ++c4) {
+		const uint32_t w = valid ? wnext - 0x21212121u : 0u;
+		if (c4 + 1 < L.C4) wnext = ld_stream_u32(xp + (uint64_t) (c4 + 1) * L.P);
+		uint32_t outw = 0, qvw = 0;
+		qz_word<DMODE, WANT_QV, PH>(q, w, outw, qvw);
+		st_stream_u32(yp + (uint64_t) c4 * L.P, outw);
+		if (WANT_QV) st_stream_u32(qp + (uint64_t) c4 * L.P, qvw + 0x21212121u);
+	}
+}
+
+template <int DMODE, bool WANT_QV>
 __global__ void __launch_bounds__(QZ_THREADS, QZ_BLOCKS_PER_SM)
 qvz_quantize_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint8_t *__restrict__ cl,
                     const uint32_t *__restrict__ W, const uint8_t *__restrict__ R,
@@ -44,82 +137,69 @@ qvz_quantize_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint8_t
                     uint32_t *__restrict__ Yw, uint32_t *__restrict__ Qw, double *__restrict__ Ep,
                     int *__restrict__ flags)
 {
-	__shared__ uint32_t ws[32 * QZ_THREADS];         // WELL state, word k of thread t at ws[k*256 + t]
-	__shared__ double dd[QVZ_ALPHABET];              // distortion as a function of |x - y| (TOEPLITZ only)
+	extern __shared__ __align__(16) uint32_t smem[];  // WELL ring [32][256], then the |x-y| distortion table
 	const uint32_t t = threadIdx.x;
 	const uint64_t r = (uint64_t) blockIdx.x * QZ_THREADS + t;      // run index, < T (T % 256 == 0)
 #pragma unroll
-	for (int k = 0; k < 32; ++k) ws[k * QZ_THREADS + t] = run_states[r * 32 + k];
-	if (TOEPLITZ) {
-		if (t < QVZ_ALPHABET) dd[t] = D[t];          // D[x + 72*0] = f(|x|)
-		__syncthreads();
-	}
-	uint32_t n = 0;                                  // ring index: uniform, every thread steps in lockstep
-	uint32_t bits = 0, left = 0;
+	for (int k = 0; k < 32; ++k) smem[k * QZ_THREADS + t] = run_states[r * 32 + k];
+	double *dd = (double *) (smem + QZ_WS_WORDS);
+	uint32_t *di = smem + QZ_WS_WORDS;
+	if (DMODE == 1 && t < QVZ_ALPHABET) dd[t] = D[t];               // D[x + 72*0] = f(|x - 0|)
+	if (DMODE == 2 && t < QVZ_ALPHABET) di[t] = (uint32_t) D[t];
+	if (DMODE != 0) __syncthreads();
+
+	qz_ctx q;
+	q.W = W;
+	q.R = R;
+	q.D = D;
+	q.ws = smem + t;
+	q.dd = dd;
+	q.di = di;
+	q.n10 = 0;
+	q.bits = 0;
 	bool missing = false;
-	const uint32_t C = L.C, C4 = L.C4;
+	const uint32_t C = L.C, full = C >> 2, rem = C & 3;
 
 	for (uint32_t i = 0; i < L.Lr; ++i) {
 		const uint64_t p = (uint64_t) i * L.T + r;
 		const uint32_t kraw = cl[p];
 		const bool valid = kraw != QVZ_NO_LINE;
 		const uint32_t k = valid ? kraw : 0;
-		const uint32_t *Wc = W + (uint64_t) k * C * (72u * 72u);     // advances by one column table per symbol
-		const uint8_t *Rc = R + (uint64_t) k * C * 72u;
+		q.wbase = k * C * (72u * 72u);
+		q.rbase = k * C * 72u;
+		q.prev = 0;
+		q.maxratio = 0;
+		q.erri = 0;
+		q.errd = 0.0;                                // 0.0 + d == d exactly: same bits as "error = d" at column 0
 		const uint32_t *xp = Xw + p;
 		uint32_t *yp = Yw + p;
-		uint32_t *qp = Qw ? Qw + p : nullptr;
-		uint32_t prev = 0;
-		double err = 0.0;                            // 0.0 + d == d exactly: same bits as "error = d" at column 0
+		uint32_t *qp = WANT_QV ? Qw + p : nullptr;
 		uint32_t wnext = ld_stream_u32(xp);
-		for (uint32_t c4 = 0; c4 < C4; ++c4) {
-			const uint32_t w = valid ? wnext - 0x21212121u : 0u;
-			if (c4 + 1 < C4) wnext = ld_stream_u32(xp + (uint64_t) (c4 + 1) * L.P);
-			uint32_t outw = 0, qvw = 0;
-#pragma unroll
-			for (uint32_t j = 0; j < 4; ++j) {
-				if (4 * c4 + j < C) {
-					if (left < 7) {                  // well_1024a_bits refill (src/well.c:37-40)
-						const uint32_t z0 = ws[((n + 31) & 31) * QZ_THREADS + t];
-						const uint32_t a = ws[((n + 3) & 31) * QZ_THREADS + t];
-						const uint32_t b = ws[((n + 24) & 31) * QZ_THREADS + t];
-						const uint32_t c = ws[((n + 10) & 31) * QZ_THREADS + t];
-						const uint32_t z1 = ws[n * QZ_THREADS + t] ^ (a ^ (a >> 8));
-						const uint32_t z2 = (b ^ (b << 19)) ^ (c ^ (c << 14));
-						ws[n * QZ_THREADS + t] = z1 ^ z2;
-						n = (n + 31) & 31;
-						bits = (z0 ^ (z0 << 11)) ^ (z1 ^ (z1 << 7)) ^ (z2 ^ (z2 << 13));
-						ws[n * QZ_THREADS + t] = bits;
-						left = 32;
-					}
-					const uint32_t draw = bits & 127u;
-					bits >>= 7;
-					left -= 7;
-					const uint32_t data = (w >> (8 * j)) & 0xFFu;
-					// the two loads below depend only on prev (and on data, known long before)
-					const uint32_t e = __ldg(Wc + prev * 72u + data);
-					const uint32_t ratio = __ldg(Rc + prev);
-					missing |= valid && (ratio == 0xFFu);
-					const uint32_t hi = draw >= ratio;
-					const uint32_t qv = __byte_perm(e, 0, hi) & 0xFFu;           // byte hi of e
-					const uint32_t st = __byte_perm(e, 0, 2 + hi) & 0xFFu;       // byte 2+hi of e
-					outw |= (st | (hi << 7)) << (8 * j);
-					qvw |= (qv + 33u) << (8 * j);
-					if (TOEPLITZ) {
-						const int df = (int) data - (int) qv;
-						err += dd[df < 0 ? -df : df];
-					} else {
-						err += __ldg(&D[data + 72u * qv]);
-					}
-					prev = qv;
-					Wc += 72u * 72u;
-					Rc += 72u;
-				}
-			}
-			st_stream_u32(yp + (uint64_t) c4 * L.P, outw);
-			if (qp) st_stream_u32(qp + (uint64_t) c4 * L.P, qvw);
+		const uint32_t ph = (i * C) & 3;             // uniform: where in its WELL word this line starts
+		switch (ph) {
+		case 0: qz_full_words<DMODE, WANT_QV, 0>(q, L, valid, xp, yp, qp, full, wnext); break;
+		case 1: qz_full_words<DMODE, WANT_QV, 1>(q, L, valid, xp, yp, qp, full, wnext); break;
+		case 2: qz_full_words<DMODE, WANT_QV, 2>(q, L, valid, xp, yp, qp, full, wnext); break;
+		default: qz_full_words<DMODE, WANT_QV, 3>(q, L, valid, xp, yp, qp, full, wnext); break;
 		}
-		if (Ep) Ep[p] = err / (double) C;
+		if (rem) {                                   // last, partial word of the line
+			const uint32_t w = valid ? wnext - 0x21212121u : 0u;
+			uint32_t outw = 0, qvw = 0;
+			if (ph == 0) qz_refill(q);
+			qz_symbol<DMODE, WANT_QV, 0>(q, w, outw, qvw);
+			if (rem > 1) {
+				if (ph == 3) qz_refill(q);
+				qz_symbol<DMODE, WANT_QV, 1>(q, w, outw, qvw);
+			}
+			if (rem > 2) {
+				if (ph == 2) qz_refill(q);
+				qz_symbol<DMODE, WANT_QV, 2>(q, w, outw, qvw);
+			}
+			st_stream_u32(yp + (uint64_t) full * L.P, outw);
+			if (WANT_QV) st_stream_u32(qp + (uint64_t) full * L.P, qvw + 0x21212121u);
+		}
+		missing |= valid && (q.maxratio == 0xFFu);
+		if (Ep) Ep[p] = (DMODE == 2 ? (double) q.erri : q.errd) / (double) C;
 	}
 	if (missing) atomicOr(&flags[2], 1);
 }
@@ -146,7 +226,8 @@ qvz_quantize_compose_kernel(uint32_t KC, const uint32_t *__restrict__ nctx, cons
 			if (lo >= 72 || hi >= 72) {
 				atomicOr(&flags[3], 1);
 			} else {
-				e = lo | (hi << 8) | ((uint32_t) (smap[q * 72 + lo] & 0x7F) << 16) | ((uint32_t) (smap[(q + 1) * 72 + hi] & 0x7F) << 24);
+				e = lo | (hi << 8) | ((uint32_t) (smap[q * 72 + lo] & 0x7F) << 16) |
+				    ((uint32_t) ((smap[(q + 1) * 72 + hi] & 0x7F) | 0x80) << 24);
 			}
 			if (x == 0) R[kc * 72 + v] = qratio[q_off[kc] / 2 + ctx];
 		}
@@ -166,18 +247,26 @@ int qvz_quantize_compose(qvz_gpu *h, uint32_t KC, const uint32_t *nctx, const ui
 	return QVZ_OK;
 }
 
-int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int toeplitz) {
-	const unsigned grid = h->L.T / QZ_THREADS;
-	// leave ~100 KB of L1 for the table band: 4 CTAs x 33 KB of shared memory
-	const int carve = 60;
-	if (toeplitz) {
-		cudaFuncSetAttribute(qvz_quantize_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-		qvz_quantize_kernel<true><<<grid, QZ_THREADS, 0, h->stream>>>(h->L, h->Xw, h->cl, h->W, h->R, h->D, h->run_states, h->Yw,
-		                                                              want_qv ? h->Qw : nullptr, want_err ? h->Ep : nullptr, h->flags);
+template <int DMODE, bool WANT_QV>
+static void launch_quantize(qvz_gpu *h, int want_err) {
+	auto kern = qvz_quantize_kernel<DMODE, WANT_QV>;
+	const size_t smem = QZ_WS_WORDS * sizeof(uint32_t) + QVZ_ALPHABET * sizeof(double);
+	// leave ~100 KB of L1 for the table band: 4 CTAs x ~33 KB of shared memory
+	cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+	kern<<<h->L.T / QZ_THREADS, QZ_THREADS, smem, h->stream>>>(h->L, h->Xw, h->cl, h->W, h->R, h->D, h->run_states, h->Yw,
+	                                                           WANT_QV ? h->Qw : nullptr, want_err ? h->Ep : nullptr, h->flags);
+}
+
+// dmode: 0 arbitrary matrix, 1 function of |x-y|, 2 integer-valued function of |x-y|
+int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int dmode) {
+	if (want_qv) {
+		if (dmode == 2) launch_quantize<2, true>(h, want_err);
+		else if (dmode == 1) launch_quantize<1, true>(h, want_err);
+		else launch_quantize<0, true>(h, want_err);
 	} else {
-		cudaFuncSetAttribute(qvz_quantize_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-		qvz_quantize_kernel<false><<<grid, QZ_THREADS, 0, h->stream>>>(h->L, h->Xw, h->cl, h->W, h->R, h->D, h->run_states, h->Yw,
-		                                                               want_qv ? h->Qw : nullptr, want_err ? h->Ep : nullptr, h->flags);
+		if (dmode == 2) launch_quantize<2, false>(h, want_err);
+		else if (dmode == 1) launch_quantize<1, false>(h, want_err);
+		else launch_quantize<0, false>(h, want_err);
 	}
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());

@@ -17,6 +17,7 @@ ap.add_argument("--lines", type=int, default=4_000_000)
 ap.add_argument("--columns", type=int, default=150)
 ap.add_argument("--clusters", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--tables", default="")
 a = ap.parse_args()
 
 n, c, k = a.lines, a.columns, a.clusters
@@ -33,7 +34,11 @@ h.load_rows(rows, n, c, c + 1)
 rn = rows.numpy()
 picks = [(i * 7919 + 13) % n for i in range(k)]
 init = rn[picks, :c]
-tables = synthetic_tables(k, c, seed=3)
+if a.tables:
+    from oracle.bindings import FlatTables
+    tables = FlatTables.load(a.tables)
+else:
+    tables = synthetic_tables(k, c, seed=3)
 seed = np.full(32, 0x55555555, np.uint32)
 sym = torch.empty((n, c), dtype=torch.uint8, pin_memory=True)
 for rep in range(a.reps):
