@@ -71,7 +71,8 @@ struct qvz_gpu_timings {
 	float kmeans_assign_ms;      /* sum over iterations of the assign+accumulate kernel alone    */
 	float cond_counts_ms;        /* conditional-count kernel(s) incl. table zeroing              */
 	float quantize_setup_ms;     /* table upload + WELL jump-ahead                               */
-	float quantize_ms;           /* quantize walk kernel alone                                   */
+	float quantize_ms;           /* quantize walk: draw generation + walk kernels                */
+	float quantize_draws_ms;     /* of which: WELL draw generation kernel (0 on the line-major path) */
 	float quantize_d2h_ms;       /* output re-layout + device->host copies                       */
 	uint32_t kmeans_iters;
 	uint32_t kernel_launches;    /* kernels launched by this handle since the last reset         */

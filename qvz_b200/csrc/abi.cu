@@ -22,6 +22,7 @@ static void release_rows(qvz_gpu *h) {
 	free_dev(h->Yw); h->Yw = nullptr;
 	free_dev(h->Qw); h->Qw = nullptr;
 	free_dev(h->Ep); h->Ep = nullptr;
+	free_dev(h->Dw); h->Dw = nullptr;
 	h->K = 0;
 }
 
@@ -46,7 +47,7 @@ static float ev_ms(qvz_gpu *h, int a, int b) {
 
 // read-and-clear one device flag (after the stream has been synchronised)
 static int take_flag(qvz_gpu *h, int idx, int *value) {
-	QVZ_CUDA(h, cudaMemcpyAsync(h->h_flags, h->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->h_flags, h->flags, QVZ_NFLAGS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
 	*value = h->h_flags[idx];
 	if (*value) {
@@ -70,9 +71,9 @@ extern "C" int qvz_gpu_open(qvz_gpu **out, int device) {
 	QVZ_CUDA(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
 	QVZ_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 8; ++i) QVZ_CUDA(h, cudaEventCreate(&h->ev[i]));
-	QVZ_CUDA(h, cudaMalloc(&h->flags, 4 * sizeof(int)));
-	QVZ_CUDA(h, cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), h->stream));
-	QVZ_CUDA(h, cudaMallocHost(&h->h_flags, 4 * sizeof(int)));
+	QVZ_CUDA(h, cudaMalloc(&h->flags, QVZ_NFLAGS * sizeof(int)));
+	QVZ_CUDA(h, cudaMemsetAsync(h->flags, 0, QVZ_NFLAGS * sizeof(int), h->stream));
+	QVZ_CUDA(h, cudaMallocHost(&h->h_flags, QVZ_NFLAGS * sizeof(int)));
 	QVZ_CUDA(h, cudaMalloc(&h->D, 72 * 72 * sizeof(double)));
 	return qvz_well_init(h);
 }
@@ -86,6 +87,8 @@ extern "C" void qvz_gpu_close(qvz_gpu *h) {
 	qvz_well_free(h);
 	free_dev(h->W);
 	free_dev(h->flat);
+	free_dev(h->Wc);
+	free_dev(h->Rc);
 	free_dev(h->R);
 	free_dev(h->D);
 	free_dev(h->flags);
@@ -136,7 +139,7 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 	if (lr < 4) lr = 4;
 	L.Lr = (uint32_t) lr;
 	uint64_t runs = (n_lines + lr - 1) / lr;
-	L.T = (uint32_t) ((runs + QVZ_THREADS - 1) / QVZ_THREADS * QVZ_THREADS);
+	L.T = (uint32_t) ((runs + QVZ_RUN_ALIGN - 1) / QVZ_RUN_ALIGN * QVZ_RUN_ALIGN);
 	L.P = (uint64_t) L.T * L.Lr;
 
 	uint8_t *raw = nullptr;
@@ -144,6 +147,7 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 	QVZ_CUDA(h, cudaMalloc(&raw, raw_bytes));
 	QVZ_CUDA(h, cudaMalloc(&h->Xw, (size_t) L.C4 * L.P * sizeof(uint32_t)));
 	QVZ_CUDA(h, cudaMalloc(&h->cl, (size_t) L.P));
+	QVZ_CUDA(h, cudaMemsetAsync(h->flags + 5, 0, sizeof(int), h->stream));
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
 	QVZ_CUDA(h, cudaMemcpyAsync(raw, rows, raw_bytes, cudaMemcpyHostToDevice, h->stream));
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
@@ -157,6 +161,7 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 	rc = take_flag(h, 0, &bad);
 	cudaFree(raw);
 	if (rc) return rc;
+	h->smax = (uint32_t) h->h_flags[5];             // take_flag copied all flags back
 	h->tm.load_h2d_ms = ev_ms(h, EV_A, EV_B);
 	h->tm.load_layout_ms = ev_ms(h, EV_B, EV_C);
 	if (bad) {
@@ -411,7 +416,51 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	rc = qvz_well_run_states(h, well_seed);
 	if (rc) return rc;
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
-	rc = qvz_quantize_launch(h, qv_out != nullptr, 1, toeplitz);
+	// Fast path: compact the tables to the A x A box of values that can occur and walk column-synchronously
+	// from shared memory (quantize.cu).  A-1 = max(largest symbol in the rows, largest reachable quantized value).
+	bool batched = false;
+	uint32_t A = 0, A4 = 0;
+	{
+		const uint32_t KC = t->clusters * t->columns;
+		QVZ_CUDA(h, cudaMemsetAsync(h->flags + 4, 0, sizeof(int), h->stream));
+		rc = qvz_quantize_vmax(h, KC, h->smax);
+		if (rc) return rc;
+		QVZ_CUDA(h, cudaMemcpyAsync(h->h_flags, h->flags, QVZ_NFLAGS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+		QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+		uint32_t vmax = (uint32_t) h->h_flags[4] > h->smax ? (uint32_t) h->h_flags[4] : h->smax;
+		A = (vmax + 2) & ~1u;                        // even, >= vmax + 1
+		if (A > 72) A = 72;
+		A4 = (A + 15) & ~15u;
+		if (!getenv("QVZ_FORCE_LINE_MAJOR") && qvz_quantize_batched_smem(t->clusters, A, A4) <= 220 * 1024) {
+			batched = true;
+			const size_t wc = (size_t) KC * A * A * sizeof(uint32_t), rcb = (size_t) KC * A4;
+			if (h->Wc_cap < wc) {
+				free_dev(h->Wc);
+				h->Wc = nullptr;
+				QVZ_CUDA(h, cudaMalloc(&h->Wc, wc));
+				h->Wc_cap = wc;
+			}
+			if (h->Rc_cap < rcb) {
+				free_dev(h->Rc);
+				h->Rc = nullptr;
+				QVZ_CUDA(h, cudaMalloc(&h->Rc, rcb));
+				h->Rc_cap = rcb;
+			}
+			if (!h->Dw) QVZ_CUDA(h, cudaMalloc(&h->Dw, wbytes));
+			rc = qvz_quantize_compact(h, KC, A, A4);
+			if (rc) return rc;
+		}
+	}
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_E], h->stream));
+	if (batched) {
+		rc = qvz_quantize_draws(h);
+		if (rc) return rc;
+		QVZ_CUDA(h, cudaEventRecord(h->ev[EV_F], h->stream));
+		rc = qvz_quantize_launch_batched(h, t->clusters, A, A4, qv_out != nullptr, toeplitz);
+	} else {
+		QVZ_CUDA(h, cudaEventRecord(h->ev[EV_F], h->stream));
+		rc = qvz_quantize_launch(h, qv_out != nullptr, 1, toeplitz);
+	}
 	if (rc) return rc;
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));
 
@@ -452,8 +501,9 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	rc = take_flag(h, 3, &malformed);
 	if (rc) return rc;
 	if (malformed) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: malformed flat tables (context index or quantized value out of range)");
-	h->tm.quantize_setup_ms = ev_ms(h, EV_A, EV_B);
-	h->tm.quantize_ms = ev_ms(h, EV_B, EV_C);
+	h->tm.quantize_setup_ms = ev_ms(h, EV_A, EV_E);
+	h->tm.quantize_ms = ev_ms(h, EV_E, EV_C);
+	h->tm.quantize_draws_ms = ev_ms(h, EV_E, EV_F);
 	h->tm.quantize_d2h_ms = ev_ms(h, EV_C, EV_D);
 	if (missing) QVZ_FAIL(h, QVZ_ERR_CONTEXT, "quantize: reached a context without a quantizer (the reference asserts, src/codebook.c:164)");
 	return QVZ_OK;

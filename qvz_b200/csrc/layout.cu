@@ -18,6 +18,7 @@ qvz_ingest_kernel(qvz_layout L, const uint8_t *__restrict__ raw, uint32_t row_st
 	bool valid = line < L.n_lines;
 	const uint8_t *src = raw + line * (uint64_t) row_stride;
 	bool bad = false;
+	uint32_t mx = 33;
 	for (uint32_t c4 = 0; c4 < L.C4; ++c4) {
 		uint32_t w = 0;
 		if (valid) {
@@ -27,6 +28,7 @@ qvz_ingest_kernel(qvz_layout L, const uint8_t *__restrict__ raw, uint32_t row_st
 				if (c < L.C) {
 					uint32_t b = __ldg(src + c);
 					bad |= (b < 33u) | (b >= 33u + QVZ_ALPHABET);
+					mx = max(mx, b);
 					w |= b << (8 * j);
 				}
 			}
@@ -35,6 +37,8 @@ qvz_ingest_kernel(qvz_layout L, const uint8_t *__restrict__ raw, uint32_t row_st
 	}
 	cl[p] = valid ? 0 : QVZ_NO_LINE;
 	if (bad) atomicOr(&flags[0], 1);
+	mx = __reduce_max_sync(__activemask(), mx);
+	if ((threadIdx.x & 31) == 0) atomicMax(&flags[5], (int) mx - 33);
 }
 
 __global__ void __launch_bounds__(QVZ_THREADS)

@@ -272,3 +272,271 @@ int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int dmode) {
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;
 }
+
+// =====================================================================================================
+// Batched walk (the fast path).
+//
+// The line-major walk above keeps one WELL state per line in flight (~1000 lines per SM), and at that
+// batch size every warp-wide table load misses L1 for at least one lane, so each symbol costs an L2 round
+// trip.  The batched path splits the work:
+//
+//   qvz_draws_kernel      thread <-> run: runs the reference's WELL bit server over the run's lines and
+//                         writes the 7-bit draws, one byte per (line, column), packed like the rows:
+//                         Dw[c4][p]  (coalesced: adjacent threads hold adjacent slots).
+//   qvz_quantize_batched  one CTA walks QB_LINES slots column-synchronously.  The (cluster, column) tables
+//                         are COMPACTED to the A x A box of values that can occur (A-1 = largest symbol /
+//                         quantized value present) and staged per column in shared memory with cp.async,
+//                         double buffered, so every lookup is a shared-memory access; each thread carries
+//                         QB_LPT independent lines (ILP across the dependent prev -> lookup -> prev chains).
+// =====================================================================================================
+#define QB_THREADS 1024
+#define QB_LPT 4
+#define QB_LINES (QB_THREADS * QB_LPT)
+
+template <int PH>
+__device__ __forceinline__ uint32_t qz_draw_word(qz_ctx &q) {
+	uint32_t d = 0;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		if (((PH + j) & 3) == 0) qz_refill(q);
+		d |= (q.bits & 127u) << (8 * j);
+		q.bits >>= 7;
+	}
+	return d;
+}
+
+__global__ void __launch_bounds__(QZ_THREADS)
+qvz_draws_kernel(qvz_layout L, const uint32_t *__restrict__ run_states, uint32_t *__restrict__ Dw)
+{
+	__shared__ uint32_t ring[QZ_WS_WORDS];
+	const uint32_t t = threadIdx.x;
+	const uint64_t r = (uint64_t) blockIdx.x * QZ_THREADS + t;
+#pragma unroll
+	for (int k = 0; k < 32; ++k) ring[k * QZ_THREADS + t] = run_states[r * 32 + k];
+	qz_ctx q;
+	q.ws = ring + t;
+	q.n10 = 0;
+	q.bits = 0;
+	const uint32_t C = L.C, full = C >> 2, rem = C & 3;
+	for (uint32_t i = 0; i < L.Lr; ++i) {
+		uint32_t *dp = Dw + (uint64_t) i * L.T + r;
+		const uint32_t ph = (i * C) & 3;
+		switch (ph) {
+		case 0: for (uint32_t c4 = 0; c4 < full; ++c4) st_stream_u32(dp + (uint64_t) c4 * L.P, qz_draw_word<0>(q)); break;
+		case 1: for (uint32_t c4 = 0; c4 < full; ++c4) st_stream_u32(dp + (uint64_t) c4 * L.P, qz_draw_word<1>(q)); break;
+		case 2: for (uint32_t c4 = 0; c4 < full; ++c4) st_stream_u32(dp + (uint64_t) c4 * L.P, qz_draw_word<2>(q)); break;
+		default: for (uint32_t c4 = 0; c4 < full; ++c4) st_stream_u32(dp + (uint64_t) c4 * L.P, qz_draw_word<3>(q)); break;
+		}
+		if (rem) {
+			uint32_t d = 0;
+			for (uint32_t j = 0; j < rem; ++j) {
+				if (((ph + j) & 3) == 0) qz_refill(q);
+				d |= (q.bits & 127u) << (8 * j);
+				q.bits >>= 7;
+			}
+			st_stream_u32(dp + (uint64_t) full * L.P, d);
+		}
+	}
+}
+
+// largest quantized value any present context can emit for a data value <= smax  -> flags[4]
+__global__ void __launch_bounds__(256)
+qvz_quantize_vmax_kernel(uint64_t entries, const uint32_t *__restrict__ W, const uint8_t *__restrict__ R,
+                         uint32_t smax, int *__restrict__ vmax)
+{
+	const uint64_t idx = (uint64_t) blockIdx.x * 256 + threadIdx.x;
+	uint32_t m = 0;
+	if (idx < entries) {
+		const uint32_t x = idx % 72;
+		if (x <= smax && R[idx / 72] != 0xFF) {
+			const uint32_t e = W[idx];
+			m = max(e & 0xFFu, (e >> 8) & 0xFFu);
+		}
+	}
+	m = __reduce_max_sync(0xFFFFFFFFu, m);
+	if ((threadIdx.x & 31) == 0 && m) atomicMax(vmax, (int) m);
+}
+
+// full 72x72 tables -> A x A boxes: Wc[kc][prev][data] (A*A words), Rc[kc][prev] (A4 bytes per row block)
+__global__ void __launch_bounds__(256)
+qvz_quantize_compact_kernel(uint32_t KC, uint32_t A, uint32_t A4, const uint32_t *__restrict__ W,
+                            const uint8_t *__restrict__ R, uint32_t *__restrict__ Wc, uint8_t *__restrict__ Rc)
+{
+	const uint64_t idx = (uint64_t) blockIdx.x * 256 + threadIdx.x;
+	if (idx >= (uint64_t) KC * A * A) return;
+	const uint32_t x = idx % A, v = (idx / A) % A;
+	const uint64_t kc = idx / ((uint64_t) A * A);
+	Wc[idx] = (x < 72 && v < 72) ? W[(kc * 72 + v) * 72 + x] : 0u;
+	if (x == 0) Rc[kc * A4 + v] = v < 72 ? R[kc * 72 + v] : 0xFF;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+	const uint32_t s = (uint32_t) __cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+template <int DMODE, bool WANT_QV>
+__global__ void __launch_bounds__(QB_THREADS, 1)
+qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint32_t *__restrict__ Dw,
+                            const uint8_t *__restrict__ cl, const uint32_t *__restrict__ Wc,
+                            const uint8_t *__restrict__ Rc, const double *__restrict__ D, uint32_t K,
+                            uint32_t A, uint32_t A4, uint32_t *__restrict__ Yw, uint32_t *__restrict__ Qw,
+                            double *__restrict__ Ep, int *__restrict__ flags)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	// [dd: 72 doubles][buffer 0][buffer 1]; buffer = K*A*A table words, then (K+1)*A4 ratio bytes (row K = zeros)
+	double *dd = (double *) smem;
+	uint32_t *di = smem;
+	const uint32_t tab_words = K * A * A;
+	const uint32_t buf_words = tab_words + ((K + 1) * A4) / 4;
+	uint32_t *buf0 = smem + 2 * QVZ_ALPHABET;
+	const uint32_t tid = threadIdx.x;
+	if (DMODE == 1 && tid < QVZ_ALPHABET) dd[tid] = D[tid];
+	if (DMODE == 2 && tid < QVZ_ALPHABET) di[tid] = (uint32_t) D[tid];
+	for (uint32_t b = 0; b < 2; ++b)                 // the dummy ratio row used by slots that hold no line
+		for (uint32_t i = tid; i < A4 / 4; i += QB_THREADS) buf0[b * buf_words + tab_words + (K * A4) / 4 + i] = 0;
+	__syncthreads();
+
+	const uint32_t C = L.C, C4 = L.C4;
+	const uint32_t tab_chunks = (tab_words * 4) / 16, rt_chunks = (K * A4) / 16;
+	auto stage = [&](uint32_t col, uint32_t *dst) {  // tables of column `col`, all clusters, -> shared
+		for (uint32_t i = tid; i < tab_chunks + rt_chunks; i += QB_THREADS) {
+			if (i < tab_chunks) {
+				const uint32_t k = i / (A * A / 4), o = i - k * (A * A / 4);
+				cp_async16(dst + k * A * A + o * 4, Wc + ((uint64_t) k * C + col) * A * A + o * 4);
+			} else {
+				const uint32_t j = i - tab_chunks, k = j / (A4 / 16), o = j - k * (A4 / 16);
+				cp_async16((uint8_t *) (dst + tab_words) + k * A4 + o * 16, Rc + ((uint64_t) k * C + col) * A4 + o * 16);
+			}
+		}
+	};
+
+	bool missing = false;
+	const uint64_t nbatch = L.P / QB_LINES;
+	for (uint64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+		uint64_t p[QB_LPT];
+		uint32_t koff[QB_LPT], roff[QB_LPT], prev[QB_LPT], maxr[QB_LPT], erri[QB_LPT];
+		double errd[QB_LPT];
+		bool valid[QB_LPT];
+#pragma unroll
+		for (int j = 0; j < QB_LPT; ++j) {
+			p[j] = batch * QB_LINES + (uint64_t) j * QB_THREADS + tid;
+			const uint32_t kraw = cl[p[j]];
+			valid[j] = kraw != QVZ_NO_LINE;
+			koff[j] = valid[j] ? kraw * A * A : 0;
+			roff[j] = (valid[j] ? kraw : K) * A4;
+			prev[j] = 0;
+			maxr[j] = 0;
+			erri[j] = 0;
+			errd[j] = 0.0;
+		}
+		stage(0, buf0);
+		for (uint32_t c4 = 0; c4 < C4; ++c4) {
+			uint32_t x[QB_LPT], dr[QB_LPT], outw[QB_LPT], qvw[QB_LPT];
+#pragma unroll
+			for (int j = 0; j < QB_LPT; ++j) {
+				x[j] = ld_stream_u32(Xw + (uint64_t) c4 * L.P + p[j]);
+				dr[j] = ld_stream_u32(Dw + (uint64_t) c4 * L.P + p[j]);
+				outw[j] = 0;
+				qvw[j] = 0;
+			}
+#pragma unroll
+			for (int j = 0; j < QB_LPT; ++j) x[j] = valid[j] ? x[j] - 0x21212121u : 0u;
+#pragma unroll
+			for (int b = 0; b < 4; ++b) {
+				const uint32_t col = 4 * c4 + b;
+				if (col < C) {
+					cp_async_commit_wait_all();      // my part of column `col` has landed ...
+					__syncthreads();                 // ... everyone's has, and everyone is done with column col-1
+					if (col + 1 < C) stage(col + 1, buf0 + ((col + 1) & 1) * buf_words);
+					const uint32_t *tab = buf0 + (col & 1) * buf_words;
+					const uint8_t *rt = (const uint8_t *) (tab + tab_words);
+#pragma unroll
+					for (int j = 0; j < QB_LPT; ++j) {
+						const uint32_t draw = __byte_perm(dr[j], 0, 0x4440 + b);
+						const uint32_t data = __byte_perm(x[j], 0, 0x4440 + b);
+						const uint32_t e = tab[koff[j] + prev[j] * A + data];
+						const uint32_t ratio = rt[roff[j] + prev[j]];
+						maxr[j] = max(maxr[j], ratio);
+						const uint32_t hi = draw >= ratio;
+						const uint32_t qv = __byte_perm(e, 0, 0x4440 + hi);
+						outw[j] = __byte_perm(outw[j], e, (0x3210 & ~(0xF << (4 * b))) + ((6 + hi) << (4 * b)));
+						if (WANT_QV) qvw[j] = __byte_perm(qvw[j], e, (0x3210 & ~(0xF << (4 * b))) + ((4 + hi) << (4 * b)));
+						if (DMODE == 2) erri[j] += di[abs((int) data - (int) qv)];
+						else if (DMODE == 1) errd[j] += dd[abs((int) data - (int) qv)];
+						else errd[j] += __ldg(&D[data + 72u * qv]);
+						prev[j] = qv;
+					}
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < QB_LPT; ++j) {
+				st_stream_u32(Yw + (uint64_t) c4 * L.P + p[j], outw[j]);
+				if (WANT_QV) st_stream_u32(Qw + (uint64_t) c4 * L.P + p[j], qvw[j] + 0x21212121u);
+			}
+		}
+#pragma unroll
+		for (int j = 0; j < QB_LPT; ++j) {
+			missing |= maxr[j] == 0xFFu;             // slots without a line only ever read the zero ratio row
+			Ep[p[j]] = (DMODE == 2 ? (double) erri[j] : errd[j]) / (double) C;
+		}
+		__syncthreads();                             // the next batch restages column 0 into buffer 0
+	}
+	if (missing) atomicOr(&flags[2], 1);
+}
+
+size_t qvz_quantize_batched_smem(uint32_t K, uint32_t A, uint32_t A4) {
+	return 2 * QVZ_ALPHABET * sizeof(uint32_t) + 2 * ((size_t) K * A * A * 4 + (size_t) (K + 1) * A4);
+}
+
+int qvz_quantize_draws(qvz_gpu *h) {
+	qvz_draws_kernel<<<h->L.T / QZ_THREADS, QZ_THREADS, 0, h->stream>>>(h->L, h->run_states, h->Dw);
+	QVZ_LAUNCHED(h);
+	QVZ_CUDA(h, cudaGetLastError());
+	return QVZ_OK;
+}
+
+int qvz_quantize_vmax(qvz_gpu *h, uint32_t KC, uint32_t smax) {
+	const uint64_t entries = (uint64_t) KC * 72 * 72;
+	qvz_quantize_vmax_kernel<<<(unsigned) ((entries + 255) / 256), 256, 0, h->stream>>>(entries, h->W, h->R, smax, h->flags + 4);
+	QVZ_LAUNCHED(h);
+	QVZ_CUDA(h, cudaGetLastError());
+	return QVZ_OK;
+}
+
+int qvz_quantize_compact(qvz_gpu *h, uint32_t KC, uint32_t A, uint32_t A4) {
+	const uint64_t total = (uint64_t) KC * A * A;
+	qvz_quantize_compact_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, h->stream>>>(KC, A, A4, h->W, h->R, h->Wc, h->Rc);
+	QVZ_LAUNCHED(h);
+	QVZ_CUDA(h, cudaGetLastError());
+	return QVZ_OK;
+}
+
+template <int DMODE, bool WANT_QV>
+static void launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t A4, size_t smem) {
+	auto kern = qvz_quantize_batched_kernel<DMODE, WANT_QV>;
+	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	const uint64_t nbatch = h->L.P / QB_LINES;
+	const unsigned grid = (unsigned) (nbatch < (uint64_t) h->sm_count ? nbatch : (uint64_t) h->sm_count);
+	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->Wc, h->Rc, h->D, K, A, A4, h->Yw,
+	                                            WANT_QV ? h->Qw : nullptr, h->Ep, h->flags);
+}
+
+int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t A4, int want_qv, int dmode) {
+	const size_t smem = qvz_quantize_batched_smem(K, A, A4);
+	if (want_qv) {
+		if (dmode == 2) launch_batched<2, true>(h, K, A, A4, smem);
+		else if (dmode == 1) launch_batched<1, true>(h, K, A, A4, smem);
+		else launch_batched<0, true>(h, K, A, A4, smem);
+	} else {
+		if (dmode == 2) launch_batched<2, false>(h, K, A, A4, smem);
+		else if (dmode == 1) launch_batched<1, false>(h, K, A, A4, smem);
+		else launch_batched<0, false>(h, K, A, A4, smem);
+	}
+	QVZ_LAUNCHED(h);
+	QVZ_CUDA(h, cudaGetLastError());
+	return QVZ_OK;
+}

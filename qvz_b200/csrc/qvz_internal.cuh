@@ -20,6 +20,8 @@
 #include "../../include/qvz_gpu.h"
 
 #define QVZ_THREADS 256
+#define QVZ_RUN_ALIGN 1024    // runs per shard are a multiple of this (batched quantize: 1024 threads x 4 lines)
+#define QVZ_NFLAGS 8
 #define QVZ_NO_LINE 0xFFu
 #define QVZ_MAX_K 16            // register-resident distances in the k-means kernel
 
@@ -50,7 +52,8 @@ struct qvz_gpu {
 	uint32_t *Xw;            // [C4][P]
 	uint8_t *cl;             // [P]
 	uint32_t K;              // clusters currently installed in cl (0 = none)
-	int *flags;              // device: [0] symbol range, [1] empty cluster, [2] missing context
+	int *flags;              // device [8]: 0 symbol range, 1 empty cluster, 2 missing context, 3 malformed tables,
+	                         //             4 scratch max quantized value, 5 largest symbol (byte-33) in the rows
 	int *h_flags;            // pinned mirror
 
 	// k-means state
@@ -72,6 +75,11 @@ struct qvz_gpu {
 	size_t flat_cap;
 	uint32_t *run_states;    // [T][32] WELL state (n = 0 frame) at the first draw of each run
 	uint32_t *Yw, *Qw;       // [C4][P] packed outputs (state|hi<<7, qv+33)
+	uint32_t *Dw;            // [C4][P] packed 7-bit WELL draws, one byte per (line, column)
+	uint32_t *Wc;            // compact tables [K][C][A][A]
+	uint8_t *Rc;             // compact ratios [K][C][A4]
+	size_t Wc_cap, Rc_cap;
+	uint32_t smax;           // largest symbol value in the resident rows
 	double *Ep;              // [P] per-slot error / C
 	qvz_well_cache *well;
 
@@ -121,5 +129,10 @@ int qvz_well_jump_state(qvz_gpu *h, const uint32_t seed[32], uint64_t words, uin
 
 // quantize.cu
 int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int toeplitz);
+int qvz_quantize_draws(qvz_gpu *h);
+int qvz_quantize_vmax(qvz_gpu *h, uint32_t KC, uint32_t smax);
+int qvz_quantize_compact(qvz_gpu *h, uint32_t KC, uint32_t A, uint32_t A4);
+size_t qvz_quantize_batched_smem(uint32_t K, uint32_t A, uint32_t A4);
+int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t A4, int want_qv, int dmode);
 int qvz_quantize_compose(qvz_gpu *h, uint32_t KC, const uint32_t *nctx, const uint8_t *ctx_of, const uint64_t *q_off,
                          const uint8_t *qratio, const uint8_t *qmap, const uint8_t *smap);

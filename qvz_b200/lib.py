@@ -46,7 +46,8 @@ class Timings(C.Structure):
     """struct qvz_gpu_timings"""
     _fields_ = [("load_h2d_ms", C.c_float), ("load_layout_ms", C.c_float), ("kmeans_ms", C.c_float),
                 ("kmeans_assign_ms", C.c_float), ("cond_counts_ms", C.c_float),
-                ("quantize_setup_ms", C.c_float), ("quantize_ms", C.c_float), ("quantize_d2h_ms", C.c_float),
+                ("quantize_setup_ms", C.c_float), ("quantize_ms", C.c_float), ("quantize_draws_ms", C.c_float),
+                ("quantize_d2h_ms", C.c_float),
                 ("kmeans_iters", C.c_uint32), ("kernel_launches", C.c_uint32)]
 
     def as_dict(self):

@@ -28,7 +28,7 @@ def test_exports_match_header(libpath):
 def test_header_compiles_as_c(tmp_path):
     import subprocess
     src = tmp_path / "t.c"
-    src.write_text('#include "qvz_gpu.h"\nint main(void){struct qvz_flat_tables t; (void)t; return sizeof(struct qvz_gpu_timings) != 40;}\n')
+    src.write_text('#include "qvz_gpu.h"\nint main(void){struct qvz_flat_tables t; (void)t; return sizeof(struct qvz_gpu_timings) != 44;}\n')
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o",
                     str(tmp_path / "t")], check=True)
     subprocess.run([str(tmp_path / "t")], check=True)

@@ -26,6 +26,20 @@ def _load(gpu, rows, c):
     gpu.load_rows(rows, rows.shape[0], c, rows.shape[1])
 
 
+def _quantize_both_paths(gpu, tables, seed):
+    """The batched shared-memory walk (default) and the line-major walk must agree bit for bit."""
+    import os
+    q = gpu.quantize(tables, seed, want_qv=True, want_err=True)
+    os.environ["QVZ_FORCE_LINE_MAJOR"] = "1"
+    try:
+        q2 = gpu.quantize(tables, seed, want_qv=True, want_err=True)
+    finally:
+        del os.environ["QVZ_FORCE_LINE_MAJOR"]
+    for key in ("symbols", "qv", "line_err"):
+        assert np.array_equal(q[key], q2[key]), "paths differ: " + key
+    return q
+
+
 def test_golden_all_stages(gpu, golden):
     g = golden
     c, K = g["columns"], g["clusters"]
@@ -38,7 +52,7 @@ def test_golden_all_stages(gpu, golden):
     assert np.array_equal(r["counts"], g["kcounts"])
     assert np.array_equal(r["moved"], g["moved"])
     assert np.array_equal(gpu.cond_counts(), g["cond_counts"])
-    q = gpu.quantize(g["tables"], DEBUG_SEED, want_qv=True, want_err=True)
+    q = _quantize_both_paths(gpu, g["tables"], DEBUG_SEED)
     assert np.array_equal(q["symbols"], g["symbols"])
     assert np.array_equal(q["qv"], g["qv"])                       # the -u image, byte for byte
     assert np.array_equal(q["line_err"], g["line_err"])           # bit-exact doubles
@@ -89,7 +103,7 @@ def test_quantize_vs_oracle_synthetic_tables(gpu, oracle, n, c, k, dist):
     seed = np.random.default_rng(c).integers(0, 2**31, 32, dtype=np.uint32)
     _load(gpu, rows, c)
     gpu.set_clusters(k, ids)
-    q = gpu.quantize(t, seed, want_qv=True, want_err=True)
+    q = _quantize_both_paths(gpu, t, seed)
     o = oracle.quantize(rows, c, ids, t, seed)
     assert np.array_equal(q["symbols"], o["symbols"])
     assert np.array_equal(q["qv"], o["qv"])
@@ -106,7 +120,7 @@ def test_quantize_shard_offset(gpu, oracle):
     tail = np.ascontiguousarray(rows[L0:])
     gpu.load_rows(tail, n - L0, c, c + 1, first_line=L0)
     gpu.set_clusters(k, ids[L0:])
-    q = gpu.quantize(t, DEBUG_SEED, want_qv=True, want_err=True)
+    q = _quantize_both_paths(gpu, t, DEBUG_SEED)
     assert np.array_equal(q["symbols"], whole["symbols"][L0:])
     assert np.array_equal(q["qv"], whole["qv"][L0:])
     assert np.array_equal(q["line_err"], whole["line_err"][L0:])
@@ -128,7 +142,7 @@ def test_against_compiled_reference(gpu, ref):
     assert np.array_equal(gpu.cond_counts(), counts)
     t = s.tables()
     rq = s.quantize(DEBUG_SEED)
-    q = gpu.quantize(t, DEBUG_SEED, want_qv=True, want_err=True)
+    q = _quantize_both_paths(gpu, t, DEBUG_SEED)
     assert np.array_equal(q["symbols"], rq["symbols"])
     assert np.array_equal(q["qv"], rq["qv"])
     assert np.array_equal(q["line_err"], rq["line_err"])
