@@ -87,8 +87,7 @@ extern "C" void qvz_gpu_close(qvz_gpu *h) {
 	qvz_well_free(h);
 	free_dev(h->W);
 	free_dev(h->flat);
-	free_dev(h->Wc);
-	free_dev(h->Rc);
+	free_dev(h->G);
 	free_dev(h->R);
 	free_dev(h->D);
 	free_dev(h->flags);
@@ -431,23 +430,17 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 		A = (vmax + 2) & ~1u;                        // even, >= vmax + 1
 		if (A > 72) A = 72;
 		A4 = (A + 15) & ~15u;
-		if (!getenv("QVZ_FORCE_LINE_MAJOR") && qvz_quantize_batched_smem(t->clusters, A, A4) <= 220 * 1024) {
+		if (!getenv("QVZ_FORCE_LINE_MAJOR") && qvz_quantize_batched_group(t->clusters, A, A4) > 0) {
 			batched = true;
-			const size_t wc = (size_t) KC * A * A * sizeof(uint32_t), rcb = (size_t) KC * A4;
-			if (h->Wc_cap < wc) {
-				free_dev(h->Wc);
-				h->Wc = nullptr;
-				QVZ_CUDA(h, cudaMalloc(&h->Wc, wc));
-				h->Wc_cap = wc;
-			}
-			if (h->Rc_cap < rcb) {
-				free_dev(h->Rc);
-				h->Rc = nullptr;
-				QVZ_CUDA(h, cudaMalloc(&h->Rc, rcb));
-				h->Rc_cap = rcb;
+			const size_t gbytes = (size_t) t->columns * ((size_t) t->clusters * A * A * 4 + (size_t) t->clusters * A4);
+			if (h->G_cap < gbytes) {
+				free_dev(h->G);
+				h->G = nullptr;
+				QVZ_CUDA(h, cudaMalloc(&h->G, gbytes));
+				h->G_cap = gbytes;
 			}
 			if (!h->Dw) QVZ_CUDA(h, cudaMalloc(&h->Dw, wbytes));
-			rc = qvz_quantize_compact(h, KC, A, A4);
+			rc = qvz_quantize_compact(h, t->clusters, t->columns, A, A4);
 			if (rc) return rc;
 		}
 	}

@@ -357,17 +357,20 @@ qvz_quantize_vmax_kernel(uint64_t entries, const uint32_t *__restrict__ W, const
 	if ((threadIdx.x & 31) == 0 && m) atomicMax(vmax, (int) m);
 }
 
-// full 72x72 tables -> A x A boxes: Wc[kc][prev][data] (A*A words), Rc[kc][prev] (A4 bytes per row block)
+// full 72x72 tables -> one contiguous image per COLUMN: G[col] = { W box [K][A][A] words, ratio rows [K][A4] bytes }
 __global__ void __launch_bounds__(256)
-qvz_quantize_compact_kernel(uint32_t KC, uint32_t A, uint32_t A4, const uint32_t *__restrict__ W,
-                            const uint8_t *__restrict__ R, uint32_t *__restrict__ Wc, uint8_t *__restrict__ Rc)
+qvz_quantize_compact_kernel(uint32_t K, uint32_t C, uint32_t A, uint32_t A4, const uint32_t *__restrict__ W,
+                            const uint8_t *__restrict__ R, uint8_t *__restrict__ G)
 {
 	const uint64_t idx = (uint64_t) blockIdx.x * 256 + threadIdx.x;
-	if (idx >= (uint64_t) KC * A * A) return;
+	if (idx >= (uint64_t) K * C * A * A) return;
 	const uint32_t x = idx % A, v = (idx / A) % A;
 	const uint64_t kc = idx / ((uint64_t) A * A);
-	Wc[idx] = (x < 72 && v < 72) ? W[(kc * 72 + v) * 72 + x] : 0u;
-	if (x == 0) Rc[kc * A4 + v] = v < 72 ? R[kc * 72 + v] : 0xFF;
+	const uint32_t k = kc / C, col = kc - (uint64_t) k * C;
+	const size_t col_bytes = (size_t) K * A * A * 4 + (size_t) K * A4;
+	uint8_t *g = G + col * col_bytes;
+	((uint32_t *) g)[((size_t) k * A + v) * A + x] = (x < 72 && v < 72) ? W[(kc * 72 + v) * 72 + x] : 0u;
+	if (x == 0) g[(size_t) K * A * A * 4 + (size_t) k * A4 + v] = v < 72 ? R[kc * 72 + v] : 0xFF;
 }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -378,38 +381,41 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-template <int DMODE, bool WANT_QV>
+// S = columns staged per barrier (4, 2 or 1, whatever fits shared memory twice)
+template <int DMODE, bool WANT_QV, int S>
 __global__ void __launch_bounds__(QB_THREADS, 1)
 qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint32_t *__restrict__ Dw,
-                            const uint8_t *__restrict__ cl, const uint32_t *__restrict__ Wc,
-                            const uint8_t *__restrict__ Rc, const double *__restrict__ D, uint32_t K,
+                            const uint8_t *__restrict__ cl, const uint8_t *__restrict__ G,
+                            const double *__restrict__ D, uint32_t K,
                             uint32_t A, uint32_t A4, uint32_t *__restrict__ Yw, uint32_t *__restrict__ Qw,
                             double *__restrict__ Ep, int *__restrict__ flags)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
-	// [dd: 72 doubles][buffer 0][buffer 1]; buffer = K*A*A table words, then (K+1)*A4 ratio bytes (row K = zeros)
+	// [dd: 72 doubles][buffer 0][buffer 1]; a buffer holds S column slots; a slot = K*A*A table words, then
+	// (K+1)*A4 ratio bytes (row K = zeros, read by slots that hold no line)
 	double *dd = (double *) smem;
 	uint32_t *di = smem;
 	const uint32_t tab_words = K * A * A;
-	const uint32_t buf_words = tab_words + ((K + 1) * A4) / 4;
+	const uint32_t slot_words = tab_words + ((K + 1) * A4) / 4;
+	const uint32_t buf_words = S * slot_words;
 	uint32_t *buf0 = smem + 2 * QVZ_ALPHABET;
 	const uint32_t tid = threadIdx.x;
 	if (DMODE == 1 && tid < QVZ_ALPHABET) dd[tid] = D[tid];
 	if (DMODE == 2 && tid < QVZ_ALPHABET) di[tid] = (uint32_t) D[tid];
-	for (uint32_t b = 0; b < 2; ++b)                 // the dummy ratio row used by slots that hold no line
-		for (uint32_t i = tid; i < A4 / 4; i += QB_THREADS) buf0[b * buf_words + tab_words + (K * A4) / 4 + i] = 0;
+	for (uint32_t sl = 0; sl < 2 * S; ++sl)
+		for (uint32_t i = tid; i < A4 / 4; i += QB_THREADS) buf0[sl * slot_words + tab_words + (K * A4) / 4 + i] = 0;
 	__syncthreads();
 
 	const uint32_t C = L.C, C4 = L.C4;
-	const uint32_t tab_chunks = (tab_words * 4) / 16, rt_chunks = (K * A4) / 16;
-	auto stage = [&](uint32_t col, uint32_t *dst) {  // tables of column `col`, all clusters, -> shared
-		for (uint32_t i = tid; i < tab_chunks + rt_chunks; i += QB_THREADS) {
-			if (i < tab_chunks) {
-				const uint32_t k = i / (A * A / 4), o = i - k * (A * A / 4);
-				cp_async16(dst + k * A * A + o * 4, Wc + ((uint64_t) k * C + col) * A * A + o * 4);
-			} else {
-				const uint32_t j = i - tab_chunks, k = j / (A4 / 16), o = j - k * (A4 / 16);
-				cp_async16((uint8_t *) (dst + tab_words) + k * A4 + o * 16, Rc + ((uint64_t) k * C + col) * A4 + o * 16);
+	const uint32_t col_bytes = tab_words * 4 + K * A4;     // one column's image in G (multiple of 16)
+	auto stage = [&](uint32_t col0, uint32_t *dst) { // columns col0 .. col0+S-1 -> the S slots of dst
+#pragma unroll
+		for (int sl = 0; sl < S; ++sl) {
+			const uint32_t col = col0 + sl;
+			if (col < C) {
+				const uint8_t *src = G + (uint64_t) col * col_bytes;
+				uint8_t *d = (uint8_t *) (dst + sl * slot_words);
+				for (uint32_t o = tid * 16; o < col_bytes; o += QB_THREADS * 16) cp_async16(d + o, src + o);
 			}
 		}
 	};
@@ -417,14 +423,13 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 	bool missing = false;
 	const uint64_t nbatch = L.P / QB_LINES;
 	for (uint64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
-		uint64_t p[QB_LPT];
+		const uint64_t pbase = batch * QB_LINES + tid;   // line j of this thread: slot pbase + j*QB_THREADS
 		uint32_t koff[QB_LPT], roff[QB_LPT], prev[QB_LPT], maxr[QB_LPT], erri[QB_LPT];
 		double errd[QB_LPT];
 		bool valid[QB_LPT];
 #pragma unroll
 		for (int j = 0; j < QB_LPT; ++j) {
-			p[j] = batch * QB_LINES + (uint64_t) j * QB_THREADS + tid;
-			const uint32_t kraw = cl[p[j]];
+			const uint32_t kraw = cl[pbase + j * QB_THREADS];
 			valid[j] = kraw != QVZ_NO_LINE;
 			koff[j] = valid[j] ? kraw * A * A : 0;
 			roff[j] = (valid[j] ? kraw : K) * A4;
@@ -434,25 +439,40 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			errd[j] = 0.0;
 		}
 		stage(0, buf0);
+		uint32_t xn[QB_LPT], dn[QB_LPT];
+#pragma unroll
+		for (int j = 0; j < QB_LPT; ++j) {
+			xn[j] = ld_stream_u32(Xw + pbase + j * QB_THREADS);
+			dn[j] = ld_stream_u32(Dw + pbase + j * QB_THREADS);
+		}
 		for (uint32_t c4 = 0; c4 < C4; ++c4) {
 			uint32_t x[QB_LPT], dr[QB_LPT], outw[QB_LPT], qvw[QB_LPT];
 #pragma unroll
 			for (int j = 0; j < QB_LPT; ++j) {
-				x[j] = ld_stream_u32(Xw + (uint64_t) c4 * L.P + p[j]);
-				dr[j] = ld_stream_u32(Dw + (uint64_t) c4 * L.P + p[j]);
+				x[j] = valid[j] ? xn[j] - 0x21212121u : 0u;
+				dr[j] = dn[j];
 				outw[j] = 0;
 				qvw[j] = 0;
 			}
+			if (c4 + 1 < C4) {                           // next word's rows and draws: in flight during this word
+				const uint32_t *xr = Xw + (uint64_t) (c4 + 1) * L.P + pbase, *drw = Dw + (uint64_t) (c4 + 1) * L.P + pbase;
 #pragma unroll
-			for (int j = 0; j < QB_LPT; ++j) x[j] = valid[j] ? x[j] - 0x21212121u : 0u;
+				for (int j = 0; j < QB_LPT; ++j) {
+					xn[j] = ld_stream_u32(xr + j * QB_THREADS);
+					dn[j] = ld_stream_u32(drw + j * QB_THREADS);
+				}
+			}
 #pragma unroll
 			for (int b = 0; b < 4; ++b) {
 				const uint32_t col = 4 * c4 + b;
 				if (col < C) {
-					cp_async_commit_wait_all();      // my part of column `col` has landed ...
-					__syncthreads();                 // ... everyone's has, and everyone is done with column col-1
-					if (col + 1 < C) stage(col + 1, buf0 + ((col + 1) & 1) * buf_words);
-					const uint32_t *tab = buf0 + (col & 1) * buf_words;
+					if ((b % S) == 0) {
+						const uint32_t grp = col / S;
+						cp_async_commit_wait_all();  // my chunks of this column group have landed ...
+						__syncthreads();             // ... everyone's have, and everyone is done with the previous group
+						if (col + S < C) stage(col + S, buf0 + ((grp + 1) & 1) * buf_words);
+					}
+					const uint32_t *tab = buf0 + ((col / S) & 1) * buf_words + (b % S) * slot_words;
 					const uint8_t *rt = (const uint8_t *) (tab + tab_words);
 #pragma unroll
 					for (int j = 0; j < QB_LPT; ++j) {
@@ -472,24 +492,34 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 					}
 				}
 			}
+			uint32_t *yr = Yw + (uint64_t) c4 * L.P + pbase;
 #pragma unroll
-			for (int j = 0; j < QB_LPT; ++j) {
-				st_stream_u32(Yw + (uint64_t) c4 * L.P + p[j], outw[j]);
-				if (WANT_QV) st_stream_u32(Qw + (uint64_t) c4 * L.P + p[j], qvw[j] + 0x21212121u);
+			for (int j = 0; j < QB_LPT; ++j) st_stream_u32(yr + j * QB_THREADS, outw[j]);
+			if (WANT_QV) {
+				uint32_t *qr = Qw + (uint64_t) c4 * L.P + pbase;
+#pragma unroll
+				for (int j = 0; j < QB_LPT; ++j) st_stream_u32(qr + j * QB_THREADS, qvw[j] + 0x21212121u);
 			}
 		}
 #pragma unroll
 		for (int j = 0; j < QB_LPT; ++j) {
 			missing |= maxr[j] == 0xFFu;             // slots without a line only ever read the zero ratio row
-			Ep[p[j]] = (DMODE == 2 ? (double) erri[j] : errd[j]) / (double) C;
+			Ep[pbase + j * QB_THREADS] = (DMODE == 2 ? (double) erri[j] : errd[j]) / (double) C;
 		}
-		__syncthreads();                             // the next batch restages column 0 into buffer 0
+		__syncthreads();                             // the next batch restages group 0 into buffer 0
 	}
 	if (missing) atomicOr(&flags[2], 1);
 }
 
-size_t qvz_quantize_batched_smem(uint32_t K, uint32_t A, uint32_t A4) {
-	return 2 * QVZ_ALPHABET * sizeof(uint32_t) + 2 * ((size_t) K * A * A * 4 + (size_t) (K + 1) * A4);
+static size_t batched_smem(uint32_t K, uint32_t A, uint32_t A4, uint32_t S) {
+	return 2 * QVZ_ALPHABET * sizeof(uint32_t) + 2 * (size_t) S * ((size_t) K * A * A * 4 + (size_t) (K + 1) * A4);
+}
+
+// columns staged per barrier: the largest of 4, 2, 1 whose double buffer fits; 0 = batched path unusable
+uint32_t qvz_quantize_batched_group(uint32_t K, uint32_t A, uint32_t A4) {
+	for (uint32_t S = 4; S >= 1; S >>= 1)
+		if (batched_smem(K, A, A4, S) <= 200 * 1024) return S;
+	return 0;
 }
 
 int qvz_quantize_draws(qvz_gpu *h) {
@@ -507,34 +537,42 @@ int qvz_quantize_vmax(qvz_gpu *h, uint32_t KC, uint32_t smax) {
 	return QVZ_OK;
 }
 
-int qvz_quantize_compact(qvz_gpu *h, uint32_t KC, uint32_t A, uint32_t A4) {
-	const uint64_t total = (uint64_t) KC * A * A;
-	qvz_quantize_compact_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, h->stream>>>(KC, A, A4, h->W, h->R, h->Wc, h->Rc);
+int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, uint32_t A4) {
+	const uint64_t total = (uint64_t) K * C * A * A;
+	qvz_quantize_compact_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, h->stream>>>(K, C, A, A4, h->W, h->R, h->G);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;
 }
 
-template <int DMODE, bool WANT_QV>
-static void launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t A4, size_t smem) {
-	auto kern = qvz_quantize_batched_kernel<DMODE, WANT_QV>;
+template <int DMODE, bool WANT_QV, int S>
+static void launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t A4) {
+	auto kern = qvz_quantize_batched_kernel<DMODE, WANT_QV, S>;
+	const size_t smem = batched_smem(K, A, A4, S);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	const uint64_t nbatch = h->L.P / QB_LINES;
 	const unsigned grid = (unsigned) (nbatch < (uint64_t) h->sm_count ? nbatch : (uint64_t) h->sm_count);
-	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->Wc, h->Rc, h->D, K, A, A4, h->Yw,
+	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->G, h->D, K, A, A4, h->Yw,
 	                                            WANT_QV ? h->Qw : nullptr, h->Ep, h->flags);
 }
 
+template <int DMODE, bool WANT_QV>
+static void launch_batched_s(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t A4, uint32_t S) {
+	if (S == 4) launch_batched<DMODE, WANT_QV, 4>(h, K, A, A4);
+	else if (S == 2) launch_batched<DMODE, WANT_QV, 2>(h, K, A, A4);
+	else launch_batched<DMODE, WANT_QV, 1>(h, K, A, A4);
+}
+
 int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t A4, int want_qv, int dmode) {
-	const size_t smem = qvz_quantize_batched_smem(K, A, A4);
+	const uint32_t S = qvz_quantize_batched_group(K, A, A4);
 	if (want_qv) {
-		if (dmode == 2) launch_batched<2, true>(h, K, A, A4, smem);
-		else if (dmode == 1) launch_batched<1, true>(h, K, A, A4, smem);
-		else launch_batched<0, true>(h, K, A, A4, smem);
+		if (dmode == 2) launch_batched_s<2, true>(h, K, A, A4, S);
+		else if (dmode == 1) launch_batched_s<1, true>(h, K, A, A4, S);
+		else launch_batched_s<0, true>(h, K, A, A4, S);
 	} else {
-		if (dmode == 2) launch_batched<2, false>(h, K, A, A4, smem);
-		else if (dmode == 1) launch_batched<1, false>(h, K, A, A4, smem);
-		else launch_batched<0, false>(h, K, A, A4, smem);
+		if (dmode == 2) launch_batched_s<2, false>(h, K, A, A4, S);
+		else if (dmode == 1) launch_batched_s<1, false>(h, K, A, A4, S);
+		else launch_batched_s<0, false>(h, K, A, A4, S);
 	}
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());

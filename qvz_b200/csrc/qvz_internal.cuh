@@ -76,9 +76,8 @@ struct qvz_gpu {
 	uint32_t *run_states;    // [T][32] WELL state (n = 0 frame) at the first draw of each run
 	uint32_t *Yw, *Qw;       // [C4][P] packed outputs (state|hi<<7, qv+33)
 	uint32_t *Dw;            // [C4][P] packed 7-bit WELL draws, one byte per (line, column)
-	uint32_t *Wc;            // compact tables [K][C][A][A]
-	uint8_t *Rc;             // compact ratios [K][C][A4]
-	size_t Wc_cap, Rc_cap;
+	uint8_t *G;              // compact tables, one image per column: { W box [K][A][A] u32, ratios [K][A4] u8 }
+	size_t G_cap;
 	uint32_t smax;           // largest symbol value in the resident rows
 	double *Ep;              // [P] per-slot error / C
 	qvz_well_cache *well;
@@ -131,8 +130,8 @@ int qvz_well_jump_state(qvz_gpu *h, const uint32_t seed[32], uint64_t words, uin
 int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int toeplitz);
 int qvz_quantize_draws(qvz_gpu *h);
 int qvz_quantize_vmax(qvz_gpu *h, uint32_t KC, uint32_t smax);
-int qvz_quantize_compact(qvz_gpu *h, uint32_t KC, uint32_t A, uint32_t A4);
-size_t qvz_quantize_batched_smem(uint32_t K, uint32_t A, uint32_t A4);
+int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, uint32_t A4);
+uint32_t qvz_quantize_batched_group(uint32_t K, uint32_t A, uint32_t A4);
 int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t A4, int want_qv, int dmode);
 int qvz_quantize_compose(qvz_gpu *h, uint32_t KC, const uint32_t *nctx, const uint8_t *ctx_of, const uint64_t *q_off,
                          const uint8_t *qratio, const uint8_t *qmap, const uint8_t *smap);
