@@ -373,15 +373,31 @@ qvz_quantize_compact_kernel(uint32_t K, uint32_t C, uint32_t A, uint32_t A4, con
 	if (x == 0) g[(size_t) K * A * A * 4 + (size_t) k * A4 + v] = v < 72 ? R[kc * 72 + v] : 0xFF;
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-	const uint32_t s = (uint32_t) __cvta_generic_to_shared(smem_dst);
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc));
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a): one elected thread moves a whole column-group image
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// S = columns staged per barrier (4, 2 or 1, whatever fits shared memory twice)
+// S = columns staged per barrier (4, 2 or 1: the largest whose double buffer fits shared memory)
 template <int DMODE, bool WANT_QV, int S>
 __global__ void __launch_bounds__(QB_THREADS, 1)
 qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint32_t *__restrict__ Dw,
@@ -391,33 +407,34 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
                             double *__restrict__ Ep, int *__restrict__ flags)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
-	// [dd: 72 doubles][buffer 0][buffer 1]; a buffer holds S column slots; a slot = K*A*A table words, then
-	// (K+1)*A4 ratio bytes (row K = zeros, read by slots that hold no line)
+	// [dd: 72 doubles][2 mbarriers][buffer 0][buffer 1]; a buffer = S consecutive column images of G, each
+	// image = K*A*A table words followed by K*A4 ratio bytes
 	double *dd = (double *) smem;
 	uint32_t *di = smem;
+	uint64_t *full = (uint64_t *) (smem + 2 * QVZ_ALPHABET);
 	const uint32_t tab_words = K * A * A;
-	const uint32_t slot_words = tab_words + ((K + 1) * A4) / 4;
-	const uint32_t buf_words = S * slot_words;
-	uint32_t *buf0 = smem + 2 * QVZ_ALPHABET;
+	const uint32_t col_bytes = tab_words * 4 + K * A4;     // multiple of 16
+	const uint32_t col_words = col_bytes / 4;
+	uint32_t *buf0 = smem + 2 * QVZ_ALPHABET + 4;
+	const uint32_t buf_words = S * col_words;
 	const uint32_t tid = threadIdx.x;
 	if (DMODE == 1 && tid < QVZ_ALPHABET) dd[tid] = D[tid];
 	if (DMODE == 2 && tid < QVZ_ALPHABET) di[tid] = (uint32_t) D[tid];
-	for (uint32_t sl = 0; sl < 2 * S; ++sl)
-		for (uint32_t i = tid; i < A4 / 4; i += QB_THREADS) buf0[sl * slot_words + tab_words + (K * A4) / 4 + i] = 0;
+	if (tid == 0) {
+		mbar_init(&full[0], 1);
+		mbar_init(&full[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
 	__syncthreads();
 
 	const uint32_t C = L.C, C4 = L.C4;
-	const uint32_t col_bytes = tab_words * 4 + K * A4;     // one column's image in G (multiple of 16)
-	auto stage = [&](uint32_t col0, uint32_t *dst) { // columns col0 .. col0+S-1 -> the S slots of dst
-#pragma unroll
-		for (int sl = 0; sl < S; ++sl) {
-			const uint32_t col = col0 + sl;
-			if (col < C) {
-				const uint8_t *src = G + (uint64_t) col * col_bytes;
-				uint8_t *d = (uint8_t *) (dst + sl * slot_words);
-				for (uint32_t o = tid * 16; o < col_bytes; o += QB_THREADS * 16) cp_async16(d + o, src + o);
-			}
-		}
+	uint32_t gcount = 0;                             // column groups consumed so far (uniform): buffer = gcount & 1
+	auto stage = [&](uint32_t col0, uint32_t g) {    // thread 0: columns col0 .. min(col0+S, C)-1 -> buffer g & 1
+		const uint32_t ncol = (C - col0 < (uint32_t) S) ? C - col0 : (uint32_t) S;
+		const uint32_t bytes = ncol * col_bytes;
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this buffer are done
+		mbar_expect_tx(&full[g & 1], bytes);
+		tma_bulk_g2s(buf0 + (g & 1) * buf_words, G + (uint64_t) col0 * col_bytes, bytes, &full[g & 1]);
 	};
 
 	bool missing = false;
@@ -431,14 +448,15 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 		for (int j = 0; j < QB_LPT; ++j) {
 			const uint32_t kraw = cl[pbase + j * QB_THREADS];
 			valid[j] = kraw != QVZ_NO_LINE;
-			koff[j] = valid[j] ? kraw * A * A : 0;
-			roff[j] = (valid[j] ? kraw : K) * A4;
+			const uint32_t k = valid[j] ? kraw : 0;      // a slot without a line walks cluster 0's tables on zero data
+			koff[j] = k * A * A;
+			roff[j] = k * A4;
 			prev[j] = 0;
 			maxr[j] = 0;
 			erri[j] = 0;
 			errd[j] = 0.0;
 		}
-		stage(0, buf0);
+		if (tid == 0) stage(0, gcount);
 		uint32_t xn[QB_LPT], dn[QB_LPT];
 #pragma unroll
 		for (int j = 0; j < QB_LPT; ++j) {
@@ -467,12 +485,11 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 				const uint32_t col = 4 * c4 + b;
 				if (col < C) {
 					if ((b % S) == 0) {
-						const uint32_t grp = col / S;
-						cp_async_commit_wait_all();  // my chunks of this column group have landed ...
-						__syncthreads();             // ... everyone's have, and everyone is done with the previous group
-						if (col + S < C) stage(col + S, buf0 + ((grp + 1) & 1) * buf_words);
+						__syncthreads();             // everyone is done with the previous group: its buffer is free
+						if (tid == 0 && col + S < C) stage(col + S, gcount + 1);
+						mbar_wait(&full[gcount & 1], (gcount >> 1) & 1);   // this group's image has landed
 					}
-					const uint32_t *tab = buf0 + ((col / S) & 1) * buf_words + (b % S) * slot_words;
+					const uint32_t *tab = buf0 + (gcount & 1) * buf_words + (b % S) * col_words;
 					const uint8_t *rt = (const uint8_t *) (tab + tab_words);
 #pragma unroll
 					for (int j = 0; j < QB_LPT; ++j) {
@@ -490,6 +507,7 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 						else errd[j] += __ldg(&D[data + 72u * qv]);
 						prev[j] = qv;
 					}
+					if ((b % S) == S - 1 || col + 1 == C) gcount += 1;
 				}
 			}
 			uint32_t *yr = Yw + (uint64_t) c4 * L.P + pbase;
@@ -503,16 +521,16 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 		}
 #pragma unroll
 		for (int j = 0; j < QB_LPT; ++j) {
-			missing |= maxr[j] == 0xFFu;             // slots without a line only ever read the zero ratio row
+			missing |= valid[j] && maxr[j] == 0xFFu;
 			Ep[pbase + j * QB_THREADS] = (DMODE == 2 ? (double) erri[j] : errd[j]) / (double) C;
 		}
-		__syncthreads();                             // the next batch restages group 0 into buffer 0
+		__syncthreads();                             // the next batch restages into the other buffer's predecessor
 	}
 	if (missing) atomicOr(&flags[2], 1);
 }
 
 static size_t batched_smem(uint32_t K, uint32_t A, uint32_t A4, uint32_t S) {
-	return 2 * QVZ_ALPHABET * sizeof(uint32_t) + 2 * (size_t) S * ((size_t) K * A * A * 4 + (size_t) (K + 1) * A4);
+	return 2 * QVZ_ALPHABET * sizeof(uint32_t) + 16 + 2 * (size_t) S * ((size_t) K * A * A * 4 + (size_t) K * A4);
 }
 
 // columns staged per barrier: the largest of 4, 2, 1 whose double buffer fits; 0 = batched path unusable
