@@ -49,6 +49,9 @@ def workload(args, world):
 
 
 DIST = {"M": 2, "L": 3, "A": 1}        # include/distortion.h:7-9
+# glibc rand() after the implicit srand(1): what the reference's k-means initialisation consumes
+GLIBC_RAND_SEED1 = [1804289383, 846930886, 1681692777, 1714636915, 1957747793, 424238335, 719885386, 1649760492,
+                    596516649, 1189641421]
 
 
 def make_tables(cfg, counts=None):
@@ -138,18 +141,14 @@ def run_native(args):
         fe = None
     h = fe.h if fe else lib.Handle(local)
 
-    # initial centroids: rows picked by initialize_kmeans_clustering's rand() stream (src/cluster.c:199-200)
+    # initial centroids: the rows picked by initialize_kmeans_clustering's unseeded rand() stream (src/cluster.c:199-201)
+    from qvz_b200.dist import kmeans_pick_lines
     total = n * world
-    picks = [(1804289383 % ((total + 999_999) // 1_000_000)) * 0 + (i * 104_729 + 930_886) % total for i in range(k)]
-    init = np.zeros((k, c), np.uint8)
-    for j, gl in enumerate(picks):                 # every rank needs all K initial rows: broadcast from the owner
-        owner, loc = divmod(gl, n)
-        if world > 1:
-            buf = torch.from_numpy(rows_np[loc, :c].copy()).cuda() if owner == rank else torch.empty(c, dtype=torch.uint8, device="cuda")
-            dist.broadcast(buf, owner)
-            init[j] = buf.cpu().numpy()
-        else:
-            init[j] = rows_np[loc, :c]
+    picks = kmeans_pick_lines(total, k, GLIBC_RAND_SEED1)
+    if fe:
+        init = fe.broadcast_init_means(picks, rows_np, first_line, c)
+    else:
+        init = np.ascontiguousarray(rows_np[picks, :c])
     seed = np.full(32, 0x55555555, np.uint32)      # the reference's DEBUG seed (src/qv_stream.c:82)
 
     # resident inputs + tables (outside the timed region)
@@ -182,7 +181,10 @@ def run_native(args):
             h.kmeans(init, cfg.get("threshold", 4.0), want_ids=False)
             h.cond_counts(want=False)
         h.quantize(tstruct, seed, want_symbols=False)
-        return h.timings()
+        tm = h.timings()
+        if fe:                                     # the stepping calls are timed by the sharded front end
+            tm["kmeans_ms"], tm["kmeans_assign_ms"], tm["kmeans_iters"] = fe.kmeans_ms, fe.kmeans_assign_ms, km["iters"]
+        return tm
 
     def step_e2e():
         h.load_rows(rows, n, c, c + 1, first_line=first_line)

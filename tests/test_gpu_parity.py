@@ -168,3 +168,53 @@ def test_error_paths(gpu):
     assert e.value.code == 5
     with pytest.raises(QvzError):                 # shards must start on a WELL word boundary
         gpu.load_rows(rows, 64, 8, 9, first_line=2)
+
+
+def test_sharded_equals_whole(gpu, oracle):
+    """Two shards (two handles on this GPU) driven through the stepping interface, with the all-reduce of
+    the integer sums emulated by adding the two device buffers: every result equals the whole-file run."""
+    import torch
+    from qvz_b200 import lib
+    from qvz_b200.dist import shard_bounds
+    n, c, k, thr = 50_003, 37, 3, 4.0
+    rows = synth_rows(n, c, seed=41).numpy()
+    picks = [(i * 7919 + 13) % n for i in range(k)]
+    init = rows[picks, :c]
+    whole = oracle.kmeans(rows, c, init, thr)
+    b = shard_bounds(n, 2)
+    hs = [lib.Handle(0), lib.Handle(0)]
+    try:
+        for r, h in enumerate(hs):
+            h.load_rows(np.ascontiguousarray(rows[b[r]:b[r + 1]]), b[r + 1] - b[r], c, c + 1, first_line=b[r])
+            h.kmeans_begin(init)
+        sums = [torch.zeros(k * c + k, dtype=torch.int64, device="cuda") for _ in hs]
+        iters, loop = 0, True
+        while loop and iters < 1000:
+            for h, s in zip(hs, sums):
+                h.kmeans_assign_dev(s.data_ptr())
+            torch.cuda.synchronize()
+            tot = sums[0] + sums[1]
+            for s in sums:
+                s.copy_(tot)
+            torch.cuda.synchronize()
+            moved = [h.kmeans_update_dev(s.data_ptr())[0] for h, s in zip(hs, sums)]
+            assert np.array_equal(moved[0], moved[1])
+            loop = moved[0].max() > thr
+            iters += 1
+        assert iters == whole["iters"]
+        ids = np.concatenate([h.kmeans_end()[0] for h in hs])
+        assert np.array_equal(ids, whole["ids"])
+        cnt = [torch.zeros(h.cond_counts_len(), dtype=torch.int32, device="cuda") for h in hs]
+        for h, t in zip(hs, cnt):
+            h.cond_counts_dev(t.data_ptr())
+        torch.cuda.synchronize()
+        got = (cnt[0] + cnt[1]).cpu().numpy().view(np.uint32).reshape(k, 1 + 72 * (c - 1), 72)
+        assert np.array_equal(got, oracle.cond_counts(rows, c, k, whole["ids"]))
+        t = synthetic_tables(k, c, seed=2)
+        wq = oracle.quantize(rows, c, whole["ids"], t, DEBUG_SEED)
+        q = [h.quantize(t, DEBUG_SEED, want_qv=True, want_err=True) for h in hs]
+        for key in ("symbols", "qv", "line_err"):
+            assert np.array_equal(np.concatenate([x[key] for x in q]), wq[key]), key
+    finally:
+        for h in hs:
+            h.close()
