@@ -7,7 +7,8 @@
 
 #include "qvz_internal.cuh"
 
-#define QVZ_TARGET_RUNS (148u * 1024u)     // ~one resident quantize thread per run on a 148-SM B200
+#define QVZ_TARGET_RUNS (148u * 512u)      // runs per shard: enough threads for the draw generator, few enough that the
+                                           // WELL jump-ahead (one F2 mat-vec per run) stays cheap
 
 enum { EV_A = 0, EV_B, EV_C, EV_D, EV_E, EV_F };
 
@@ -133,9 +134,11 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 	L.first_line = first_line;
 	L.C = columns;
 	L.C4 = (columns + 3) / 4;
-	uint64_t lr = (n_lines + QVZ_TARGET_RUNS - 1) / QVZ_TARGET_RUNS;
-	lr = (lr + 3) & ~3ull;
-	if (lr < 4) lr = 4;
+	uint64_t target_runs = QVZ_TARGET_RUNS;
+	if (const char *e = getenv("QVZ_TARGET_RUNS")) target_runs = strtoull(e, nullptr, 10) ? strtoull(e, nullptr, 10) : target_runs;   // tuning knob
+	uint64_t lr = (n_lines + target_runs - 1) / target_runs;
+	lr = (lr + 15) & ~15ull;                      // multiple of 4: runs start on WELL word boundaries; of 16: P % 4096 == 0
+	if (lr < 16) lr = 16;
 	L.Lr = (uint32_t) lr;
 	uint64_t runs = (n_lines + lr - 1) / lr;
 	L.T = (uint32_t) ((runs + QVZ_RUN_ALIGN - 1) / QVZ_RUN_ALIGN * QVZ_RUN_ALIGN);
@@ -418,7 +421,7 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	// Fast path: compact the tables to the A x A box of values that can occur and walk column-synchronously
 	// from shared memory (quantize.cu).  A-1 = max(largest symbol in the rows, largest reachable quantized value).
 	bool batched = false;
-	uint32_t A = 0, A4 = 0;
+	uint32_t A = 0;
 	{
 		const uint32_t KC = t->clusters * t->columns;
 		QVZ_CUDA(h, cudaMemsetAsync(h->flags + 4, 0, sizeof(int), h->stream));
@@ -429,10 +432,9 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 		uint32_t vmax = (uint32_t) h->h_flags[4] > h->smax ? (uint32_t) h->h_flags[4] : h->smax;
 		A = (vmax + 2) & ~1u;                        // even, >= vmax + 1
 		if (A > 72) A = 72;
-		A4 = (A + 15) & ~15u;
-		if (!getenv("QVZ_FORCE_LINE_MAJOR") && qvz_quantize_batched_group(t->clusters, A, A4) > 0) {
+		if (!getenv("QVZ_FORCE_LINE_MAJOR") && qvz_quantize_batched_group(t->clusters, A) > 0) {
 			batched = true;
-			const size_t gbytes = (size_t) t->columns * ((size_t) t->clusters * A * A * 4 + (size_t) t->clusters * A4);
+			const size_t gbytes = (size_t) t->columns * t->clusters * A * A * 8;
 			if (h->G_cap < gbytes) {
 				free_dev(h->G);
 				h->G = nullptr;
@@ -440,7 +442,7 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 				h->G_cap = gbytes;
 			}
 			if (!h->Dw) QVZ_CUDA(h, cudaMalloc(&h->Dw, wbytes));
-			rc = qvz_quantize_compact(h, t->clusters, t->columns, A, A4);
+			rc = qvz_quantize_compact(h, t->clusters, t->columns, A);
 			if (rc) return rc;
 		}
 	}
@@ -449,7 +451,7 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 		rc = qvz_quantize_draws(h);
 		if (rc) return rc;
 		QVZ_CUDA(h, cudaEventRecord(h->ev[EV_F], h->stream));
-		rc = qvz_quantize_launch_batched(h, t->clusters, A, A4, qv_out != nullptr, toeplitz);
+		rc = qvz_quantize_launch_batched(h, t->clusters, A, qv_out != nullptr, toeplitz);
 	} else {
 		QVZ_CUDA(h, cudaEventRecord(h->ev[EV_F], h->stream));
 		rc = qvz_quantize_launch(h, qv_out != nullptr, 1, toeplitz);

@@ -6,85 +6,147 @@
 // with get_cond_pmf -> pmfs[1 + (c-1)*72 + prev] (src/codebook.c:116-120) and pmf_increment ->
 // counts[idx]++, total++ (src/pmf.c:211-214).  Output layout = that pmfs[] order, 72 counters per row.
 //
-// v1 mapping: one CTA owns one packed word column c4 (= 4 table columns) for a chunk of slots and up to
-// QVZ_CC_GROUP clusters; its 72x72 slices live in shared memory as packed 16-bit counter pairs
-// (chunk <= 65 280 slots so no counter can overflow); lanes <-> slots so global reads are coalesced;
-// shared atomics; non-zero counters are flushed with one global atomic each.
+// Mapping: one CTA owns one packed word column c4 (= 4 table columns) for a chunk of slots and a group of
+// clusters; its 72x72 slices live in shared memory; lanes <-> slots so global reads are coalesced; one
+// shared-memory atomic per symbol; non-zero counters are flushed with one global atomic each.
+//
+// The cost of a shared atomic is its number of conflicting lanes, and neighbouring reads agree on
+// (prev, cur) very often.  So lane L handles the 4 bytes of its word in the rotated order
+// (L&3), (L&3)+1, ... : at every step the 32 lanes are spread over the 4 column slices of the CTA and only
+// 8 of them can collide.  WIDE = 32-bit counters (K <= 2: no two bins share a word); otherwise packed
+// 16-bit pairs (5 clusters per pass; a chunk is < 65 536 slots so no counter can overflow).
 #include "qvz_internal.cuh"
 
-#define QVZ_CC_GROUP 5u                         // clusters per pass: 5 * 4 * 72*72 * 2 B = 207 360 B of shared memory
-#define QVZ_CC_SLICE_WORDS (72u * 72u / 2u)      // 2592 words per (cluster, column) slice
-#define QVZ_CC_CHUNK 65280u                      // slots per CTA (multiple of 256, < 65536)
-#define QVZ_CC_THREADS 1024
-#define QVZ_CC_UNROLL 4
+#define CC_THREADS 1024
+#define CC_BINS (72u * 72u)
+#define CC_PAD 8u                               // words between slices: the same bin of the 4 slices falls in 4 different banks
 
-__global__ void __launch_bounds__(QVZ_CC_THREADS)
-qvz_cond_counts_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint8_t *__restrict__ cl,
-                       uint32_t K, uint32_t G, uint32_t *__restrict__ counts)
+__device__ __forceinline__ uint4 cc_ldg128(const uint32_t *p) {
+	uint4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ void cc_red_shared(uint32_t addr, uint32_t v) {
+	asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// A thread takes 4 consecutive slots per iteration (16-byte loads of the word column, of the previous word
+// column and one 4-byte load of the cluster ids): 16 symbols per 3 loads.  TAIL = this word column holds
+// the last, partial word of the lines (columns past C must not be counted).
+template <bool WIDE, bool TAIL>
+__device__ __forceinline__ void cc_count_chunk(const uint32_t *__restrict__ xc, const uint32_t *__restrict__ xp,
+                                               const uint8_t *__restrict__ clp, uint32_t n, bool first, bool single,
+                                               uint32_t kbase, uint32_t G, const uint32_t (&sb)[4], const bool (&live)[4],
+                                               uint32_t rot8)
 {
-	extern __shared__ uint32_t tab[];            // [G][4][2592]
-	const uint32_t c4 = blockIdx.x;
-	const uint32_t kbase = blockIdx.z * QVZ_CC_GROUP;
-	const uint64_t p0 = (uint64_t) blockIdx.y * QVZ_CC_CHUNK;
-	const uint64_t p1 = (p0 + QVZ_CC_CHUNK < L.P) ? p0 + QVZ_CC_CHUNK : L.P;
-	const uint32_t words = G * 4 * QVZ_CC_SLICE_WORDS;
-
-	for (uint32_t i = threadIdx.x; i < words; i += QVZ_CC_THREADS) tab[i] = 0;
-	__syncthreads();
-
-	const uint32_t *xc = Xw + (uint64_t) c4 * L.P;
-	const uint32_t *xp = c4 ? xc - L.P : xc;
-	for (uint64_t pb = p0 + threadIdx.x; pb < p1; pb += (uint64_t) QVZ_CC_UNROLL * QVZ_CC_THREADS) {
-		uint32_t kk[QVZ_CC_UNROLL], ww[QVZ_CC_UNROLL], pp[QVZ_CC_UNROLL];
+	constexpr uint32_t SLICE = (WIDE ? CC_BINS : CC_BINS / 2) + CC_PAD;
+	for (uint32_t i = 4 * threadIdx.x; i < n; i += 4 * CC_THREADS) {
+		const uint4 w4 = cc_ldg128(xc + i);
+		const uint4 q4 = first ? make_uint4(0x21212121u, 0x21212121u, 0x21212121u, 0x21212121u) : cc_ldg128(xp + i);
+		const uint32_t k4 = single ? 0u : __ldg((const uint32_t *) (clp + i));
+		const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w}, qs[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-		for (int u = 0; u < QVZ_CC_UNROLL; ++u) {    // all loads first: 3*UNROLL independent requests in flight
-			const uint64_t p = pb + (uint64_t) u * QVZ_CC_THREADS;
-			const bool in = p < p1;
-			kk[u] = in ? cl[p] : QVZ_NO_LINE;
-			ww[u] = in ? xc[p] : 0u;
-			pp[u] = (in && c4) ? xp[p] : 0x21212121u;
-		}
+		for (int u = 0; u < 4; ++u) {
+			const uint32_t g = ((k4 >> (8 * u)) & 0xFFu) - kbase;      // wraps to a huge value for k < kbase and for 0xFF
+			if (ws[u] != 0u && g < G) {                  // a slot without a line holds zero words (real bytes are >= 33)
+				const uint32_t w = ws[u] - 0x21212121u;  // ingest guarantees every real byte >= 33: no borrow
+				const uint32_t pv = __funnelshift_r(qs[u] - 0x21212121u, w, 24);   // bytes: prev of byte 0, 1, 2, 3
+				const uint32_t wr = __funnelshift_r(w, w, rot8), pr = __funnelshift_r(pv, pv, rot8);
+				const uint32_t gb = single ? 0u : g * (4 * SLICE * 4);
+				// bins of bytes (0, 2) and (1, 3) as 16-bit pairs: prev*72 + cur <= 5183, times 4 still fits 16 bits
+				const uint32_t be = (pr & 0x00FF00FFu) * (WIDE ? 288u : 72u) + ((wr & 0x00FF00FFu) << (WIDE ? 2 : 0));
+				const uint32_t bo = ((pr >> 8) & 0x00FF00FFu) * (WIDE ? 288u : 72u) + (((wr >> 8) & 0x00FF00FFu) << (WIDE ? 2 : 0));
 #pragma unroll
-		for (int u = 0; u < QVZ_CC_UNROLL; ++u) {
-			const uint32_t g = kk[u] - kbase;        // wraps to a huge value for k < kbase and for 0xFF
-			if (g >= G) continue;
-			const uint32_t w = ww[u] - 0x21212121u;  // ingest guarantees every real byte >= 33: no borrow
-			uint32_t prev = c4 ? ((pp[u] >> 24) - 33u) : 0u;
-#pragma unroll
-			for (uint32_t j = 0; j < 4; ++j) {
-				if (4 * c4 + j < L.C) {
-					const uint32_t cur = (w >> (8 * j)) & 0xFFu;
-					const uint32_t bin = prev * 72u + cur;
-					atomicAdd(&tab[(g * 4 + j) * QVZ_CC_SLICE_WORDS + (bin >> 1)], 1u << (16 * (bin & 1)));
-					prev = cur;
+				for (uint32_t j = 0; j < 4; ++j) {
+					const uint32_t pair = (j & 1) ? bo : be;
+					const uint32_t bin = (j & 2) ? pair >> 16 : pair & 0xFFFFu;      // WIDE: byte offset of the counter
+					if (WIDE) {
+						if (!TAIL || live[j]) cc_red_shared(sb[j] + gb + bin, 1u);
+					} else {
+						const uint32_t a = sb[j] + gb + ((bin << 1) & ~3u);
+						if (!TAIL || live[j]) cc_red_shared(a, 1u << (16 * (bin & 1)));
+					}
 				}
 			}
 		}
 	}
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(CC_THREADS, 1)
+qvz_cond_counts_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint8_t *__restrict__ cl,
+                       uint32_t K, uint32_t G, uint32_t chunk, uint32_t *__restrict__ counts)
+{
+	extern __shared__ uint32_t tab[];            // [G][4][SLICE]
+	constexpr uint32_t SLICE = (WIDE ? CC_BINS : CC_BINS / 2) + CC_PAD;
+	const uint32_t c4 = blockIdx.x;
+	const uint32_t kbase = blockIdx.z * G;
+	const uint64_t p0 = (uint64_t) blockIdx.y * chunk;
+	const uint64_t p1 = (p0 + chunk < L.P) ? p0 + chunk : L.P;      // chunk % 4096 == 0 and P % 4096 == 0
+	const uint32_t words = G * 4 * SLICE;
+
+	for (uint32_t i = threadIdx.x; i < words; i += CC_THREADS) tab[i] = 0;
+	__syncthreads();
+
+	const uint32_t rot = threadIdx.x & 3;
+	const uint32_t tab_addr = (uint32_t) __cvta_generic_to_shared(tab);
+	uint32_t sb[4];                              // shared address of the slice that byte j of the ROTATED word counts into
+	bool live[4];
+#pragma unroll
+	for (uint32_t j = 0; j < 4; ++j) {
+		const uint32_t sl = (j + rot) & 3;
+		sb[j] = tab_addr + sl * SLICE * 4;
+		live[j] = 4 * c4 + sl < L.C;
+	}
+	const uint32_t *xc = Xw + (uint64_t) c4 * L.P + p0;
+	const uint32_t *xp = xc - L.P;               // only dereferenced for c4 > 0
+	const uint32_t n = (uint32_t) (p1 - p0);
+	if (4 * c4 + 3 < L.C) cc_count_chunk<WIDE, false>(xc, xp, cl + p0, n, c4 == 0, K == 1, kbase, G, sb, live, 8 * rot);
+	else cc_count_chunk<WIDE, true>(xc, xp, cl + p0, n, c4 == 0, K == 1, kbase, G, sb, live, 8 * rot);
 	__syncthreads();
 
 	const uint64_t per_cluster = (uint64_t) (1 + 72 * (L.C - 1)) * 72;
-	for (uint32_t i = threadIdx.x; i < words; i += QVZ_CC_THREADS) {
+	for (uint32_t i = threadIdx.x; i < words; i += CC_THREADS) {
 		const uint32_t v = tab[i];
 		if (!v) continue;
-		const uint32_t slice = i / QVZ_CC_SLICE_WORDS, wbin = i - slice * QVZ_CC_SLICE_WORDS;
+		const uint32_t slice = i / SLICE, wbin = i - slice * SLICE;
 		const uint32_t g = slice >> 2, j = slice & 3, col = 4 * c4 + j;
+		if (kbase + g >= K || wbin >= SLICE - CC_PAD) continue;
 		// column 0 only ever sees prev == 0 => bins 0..71 => pmfs[0]; column c >= 1 starts at pmfs[1 + (c-1)*72]
-		uint32_t *dst = counts + (uint64_t) (kbase + g) * per_cluster + (col ? (uint64_t) (1 + (col - 1) * 72) * 72 : 0) + 2 * wbin;
-		if (v & 0xFFFFu) atomicAdd(dst, v & 0xFFFFu);
-		if (v >> 16) atomicAdd(dst + 1, v >> 16);
+		uint32_t *dst = counts + (uint64_t) (kbase + g) * per_cluster + (col ? (uint64_t) (1 + (col - 1) * 72) * 72 : 0);
+		if (WIDE) {
+			atomicAdd(dst + wbin, v);
+		} else {
+			if (v & 0xFFFFu) atomicAdd(dst + 2 * wbin, v & 0xFFFFu);
+			if (v >> 16) atomicAdd(dst + 2 * wbin + 1, v >> 16);
+		}
 	}
 }
 
 int qvz_cond_counts_launch(qvz_gpu *h, uint32_t *counts_dev) {
 	const uint32_t K = h->K;
-	const uint32_t G = K < QVZ_CC_GROUP ? K : QVZ_CC_GROUP;
-	const size_t smem = (size_t) G * 4 * QVZ_CC_SLICE_WORDS * sizeof(uint32_t);
+	const bool wide = K <= 2;
+	const uint32_t G = wide ? K : (K < 5 ? K : 5);
+	const size_t smem = (size_t) G * 4 * ((wide ? CC_BINS : CC_BINS / 2) + CC_PAD) * sizeof(uint32_t);
+	// chunk: a multiple of the per-iteration stride; packed counters need < 65 536 slots per CTA; wide ones are
+	// sized for ~16 CTAs per SM over the whole grid so that zeroing/flushing the slices stays negligible
+	uint32_t chunk = 61440;
+	if (wide) {
+		const uint64_t want = (uint64_t) h->sm_count * 16 / h->L.C4 + 1;
+		uint64_t c = (h->L.P + want - 1) / want;
+		c = (c + 4095) / 4096 * 4096;
+		chunk = (uint32_t) (c < 61440 ? 61440 : c);
+	}
 	QVZ_CUDA(h, cudaMemsetAsync(counts_dev, 0, qvz_gpu_cond_counts_len(K, h->L.C) * sizeof(uint32_t), h->stream));
-	QVZ_CUDA(h, cudaFuncSetAttribute(qvz_cond_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	dim3 grid(h->L.C4, (unsigned) ((h->L.P + QVZ_CC_CHUNK - 1) / QVZ_CC_CHUNK), (K + QVZ_CC_GROUP - 1) / QVZ_CC_GROUP);
-	// the last cluster group may be partial: G applies to all groups, out-of-range ids are skipped by g >= G
-	qvz_cond_counts_kernel<<<grid, QVZ_CC_THREADS, smem, h->stream>>>(h->L, h->Xw, h->cl, K, G, counts_dev);
+	dim3 grid(h->L.C4, (unsigned) ((h->L.P + chunk - 1) / chunk), (K + G - 1) / G);
+	// the last cluster group may be partial: out-of-range ids are skipped by g >= G / kbase + g >= K
+	if (wide) {
+		QVZ_CUDA(h, cudaFuncSetAttribute(qvz_cond_counts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		qvz_cond_counts_kernel<true><<<grid, CC_THREADS, smem, h->stream>>>(h->L, h->Xw, h->cl, K, G, chunk, counts_dev);
+	} else {
+		QVZ_CUDA(h, cudaFuncSetAttribute(qvz_cond_counts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		qvz_cond_counts_kernel<false><<<grid, CC_THREADS, smem, h->stream>>>(h->L, h->Xw, h->cl, K, G, chunk, counts_dev);
+	}
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;

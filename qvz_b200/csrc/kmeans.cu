@@ -147,6 +147,56 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
 	if (tid < K && cnt[tid]) atomicAdd(&sums[(uint64_t) K * L.C + tid], (unsigned long long) cnt[tid]);
 }
 
+// K == 1: assign_cluster has nothing to compare -- every line lands in cluster 0 -- so one iteration is just
+// recalculate_means' column sums (src/cluster.c:96-104): a streaming reduction at HBM speed.
+// CTA <-> (chunk of slots, column word); a thread adds 16-byte vectors of 4 slots as packed 16-bit halves
+// (<= KS_ITERS * 4 * 255 < 2^16 per field), then warp REDUX + one 64-bit global atomic per (CTA, column).
+#define KS_THREADS 256
+#define KS_ITERS 32
+#define KS_CHUNK (KS_THREADS * 4 * KS_ITERS)
+
+__global__ void __launch_bounds__(KS_THREADS)
+qvz_kmeans_single_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t *__restrict__ cl,
+                         unsigned long long *__restrict__ sums)
+{
+	__shared__ uint32_t red[KS_THREADS / 32][4];
+	const uint32_t c4 = blockIdx.y, tid = threadIdx.x;
+	const uint64_t p0 = (uint64_t) blockIdx.x * KS_CHUNK;
+	const uint64_t p1 = (p0 + KS_CHUNK < L.P) ? p0 + KS_CHUNK : L.P;      // P % 4096 == 0: whole uint4s
+	const uint4 *src = (const uint4 *) (Xw + (uint64_t) c4 * L.P);
+	uint32_t lo = 0, hi = 0;
+#pragma unroll 8
+	for (uint64_t p = p0 + 4 * tid; p < p1; p += 4 * KS_THREADS) {
+		uint4 v;
+		asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+		             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + (p >> 2)));
+		lo += (v.x & 0x00FF00FFu) + (v.y & 0x00FF00FFu) + (v.z & 0x00FF00FFu) + (v.w & 0x00FF00FFu);
+		hi += ((v.x >> 8) & 0x00FF00FFu) + ((v.y >> 8) & 0x00FF00FFu) + ((v.z >> 8) & 0x00FF00FFu) + ((v.w >> 8) & 0x00FF00FFu);
+	}
+	if (c4 == 0) {                                   // line->cluster = 0 for every real line (0xFF marks an empty slot)
+		uint32_t *c32 = (uint32_t *) cl;
+		for (uint64_t p = p0 + 4 * tid; p < p1; p += 4 * KS_THREADS) {
+			const uint32_t v = c32[p >> 2];
+			const uint32_t nv = ((v >> 7) & 0x01010101u) * 0xFFu;      // ids are < 16: bit 7 is set only in 0xFF
+			if (nv != v) c32[p >> 2] = nv;
+		}
+	}
+	uint32_t f[4] = {lo & 0xFFFFu, hi & 0xFFFFu, lo >> 16, hi >> 16};   // bytes 0..3 of a word = columns 4*c4 .. 4*c4+3
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, f[j]);
+		if ((tid & 31) == 0) red[tid >> 5][j] = s;
+	}
+	__syncthreads();
+	if (tid < 4 && 4 * c4 + tid < L.C) {
+		unsigned long long s = 0;
+#pragma unroll
+		for (int w = 0; w < KS_THREADS / 32; ++w) s += red[w][tid];
+		if (s) atomicAdd(&sums[4 * c4 + tid], s);
+	}
+	if (blockIdx.x == 0 && c4 == 0 && tid == 0) sums[L.C] = L.n_lines;   // cluster_t.count of the only cluster
+}
+
 // recalculate_means (src/cluster.c:106-128) on the reduced sums; also repacks the centroids for dp4a.
 // first = 1: only pack the initial centroids (initialize_kmeans_clustering copied them from rows).
 __global__ void __launch_bounds__(QVZ_THREADS)
@@ -230,6 +280,13 @@ int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev) {
 	const uint64_t cap = (uint64_t) h->sm_count * (per_sm ? per_sm : 1);
 	const unsigned grid = (unsigned) (blocks < cap ? blocks : cap);
 	QVZ_CUDA(h, cudaMemsetAsync(sums_dev, 0, ((size_t) K * h->L.C + K) * sizeof(int64_t), h->stream));
+	if (K == 1) {
+		dim3 g((unsigned) ((h->L.P + KS_CHUNK - 1) / KS_CHUNK), C4);
+		qvz_kmeans_single_kernel<<<g, KS_THREADS, 0, h->stream>>>(h->L, h->Xw, h->cl, (unsigned long long *) sums_dev);
+		QVZ_LAUNCHED(h);
+		QVZ_CUDA(h, cudaGetLastError());
+		return QVZ_OK;
+	}
 	switch (K) {
 	case 1: launch_assign<1>(h, sums_dev, grid, R, smem); break;
 	case 2: launch_assign<2>(h, sums_dev, grid, R, smem); break;

@@ -32,6 +32,8 @@
 // double additions is the same exact integer); DMODE 1 = function of |x-y| (-d L): doubles from shared
 // memory added in column order (bit-identical to the reference's sequence of additions);
 // DMODE 0 = arbitrary 72x72 matrix (-D file) read from global memory.
+#include <type_traits>
+
 #include "qvz_internal.cuh"
 
 #define QZ_THREADS QVZ_THREADS
@@ -276,65 +278,111 @@ int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int dmode) {
 // =====================================================================================================
 // Batched walk (the fast path).
 //
-// The line-major walk above keeps one WELL state per line in flight (~1000 lines per SM), and at that
-// batch size every warp-wide table load misses L1 for at least one lane, so each symbol costs an L2 round
-// trip.  The batched path splits the work:
+// The line-major walk above keeps one WELL state per line in flight and its table loads go to L1/L2.  The
+// batched path splits the work in two kernels:
 //
-//   qvz_draws_kernel      thread <-> run: runs the reference's WELL bit server over the run's lines and
-//                         writes the 7-bit draws, one byte per (line, column), packed like the rows:
-//                         Dw[c4][p]  (coalesced: adjacent threads hold adjacent slots).
+//   qvz_draws_kernel      thread <-> run.  The WELL1024a state lives in 32 REGISTERS: the generator is
+//                         unrolled over one full turn of the ring (32 steps, n returns to 0) so that every
+//                         state index is a compile-time constant; the 32 words of a turn are expanded to
+//                         one byte per 7-bit draw and parked in a per-thread shared-memory FIFO, from which
+//                         the reference's bit server order (4 draws per word, low bits first, src/well.c:33-46)
+//                         is replayed line by line into Dw[c4][p], one byte per (line, column), packed like
+//                         the rows (coalesced: adjacent threads hold adjacent slots).
 //   qvz_quantize_batched  one CTA walks QB_LINES slots column-synchronously.  The (cluster, column) tables
 //                         are COMPACTED to the A x A box of values that can occur (A-1 = largest symbol /
-//                         quantized value present) and staged per column in shared memory with cp.async,
-//                         double buffered, so every lookup is a shared-memory access; each thread carries
-//                         QB_LPT independent lines (ILP across the dependent prev -> lookup -> prev chains).
+//                         quantized value present) and staged per column group in shared memory by TMA bulk
+//                         copies (double buffered, mbarrier completion), so every lookup is one LDS.64;
+//                         each thread carries QB_LPT independent lines (ILP across the dependent
+//                         prev -> lookup -> prev chains).
+//
+// Compact table image, one per column (G[col] = two planes of K*A*A words: lo quantizers, then hi quantizers):
+//   plane[hi][k][prev][data] = variant of that quantizer (the lo/hi choice is known BEFORE the lookup, so only
+//   the chosen 4-byte variant is loaded: one shared-memory wavefront when the lanes' words fall in distinct banks),   variant =
+//       byte 0  qv       the quantized value = the next column's context value (q->q[data])
+//       byte 1  |data-qv| index of the distortion table (72 = poison: NaN / 2^31, see below)
+//       byte 2  state | hi<<7      the output symbol (q->output_alphabet->indexes[qv], quantizer choice)
+//       byte 3  qratio of the NEXT column's context qv: the draw comparison of the next symbol is
+//               (draw<<24 | 0xFFFFFF) >= variant, with no field extraction at all.
+//   A context the reference would assert on (src/codebook.c:164) has poisoned entries: the line's error sum
+//   becomes NaN (double modes) or >= 2^31 (integer mode) and is reported once per line instead of being
+//   checked per symbol.
 // =====================================================================================================
 #define QB_THREADS 1024
 #define QB_LPT 4
 #define QB_LINES (QB_THREADS * QB_LPT)
+#define QB_POISON 72u
 
-template <int PH>
-__device__ __forceinline__ uint32_t qz_draw_word(qz_ctx &q) {
-	uint32_t d = 0;
-#pragma unroll
-	for (int j = 0; j < 4; ++j) {
-		if (((PH + j) & 3) == 0) qz_refill(q);
-		d |= (q.bits & 127u) << (8 * j);
-		q.bits >>= 7;
+// ---- draw generator ------------------------------------------------------------------------------------
+// one well_1024a step (src/well.c:8-24) at ring position n = (32 - T) & 31, state in registers
+template <int T>
+__device__ __forceinline__ uint32_t well_step_reg(uint32_t (&s)[32]) {
+	constexpr int n = (32 - T) & 31;
+	const uint32_t z0 = s[(n + 31) & 31], a = s[(n + 3) & 31], b = s[(n + 24) & 31], c = s[(n + 10) & 31];
+	const uint32_t z1 = s[n] ^ (a ^ (a >> 8));
+	const uint32_t z2 = (b ^ (b << 19)) ^ (c ^ (c << 14));
+	s[n] = z1 ^ z2;
+	const uint32_t out = (z0 ^ (z0 << 11)) ^ (z1 ^ (z1 << 7)) ^ (z2 ^ (z2 << 13));
+	s[(n + 31) & 31] = out;
+	return out;
+}
+
+// the 4 draws of one word (bits 0-6, 7-13, 14-20, 21-27; top 4 bits dropped) -> one byte each
+__device__ __forceinline__ uint32_t well_expand_draws(uint32_t w) {
+	w &= 0x0FFFFFFFu;
+	const uint32_t u = (w & 0x0FFFC000u) * 3u + w;       // draws 2, 3 move up by 2 bits
+	return u + (u & 0x3F803F80u);                        // draws 1, 3 move up by 1 more bit
+}
+
+template <int T>
+__device__ __forceinline__ void well_turn(uint32_t (&s)[32], uint32_t *fifo) {
+	if constexpr (T < 32) {
+		fifo[T * QZ_THREADS] = well_expand_draws(well_step_reg<T>(s));
+		well_turn<T + 1>(s, fifo);
 	}
-	return d;
 }
 
 __global__ void __launch_bounds__(QZ_THREADS)
 qvz_draws_kernel(qvz_layout L, const uint32_t *__restrict__ run_states, uint32_t *__restrict__ Dw)
 {
-	__shared__ uint32_t ring[QZ_WS_WORDS];
+	__shared__ uint32_t fifo_s[QZ_WS_WORDS];             // [32][256]: one turn of draw words per thread
 	const uint32_t t = threadIdx.x;
 	const uint64_t r = (uint64_t) blockIdx.x * QZ_THREADS + t;
+	uint32_t s[32];
 #pragma unroll
-	for (int k = 0; k < 32; ++k) ring[k * QZ_THREADS + t] = run_states[r * 32 + k];
-	qz_ctx q;
-	q.ws = ring + t;
-	q.n10 = 0;
-	q.bits = 0;
+	for (int k = 0; k < 32; ++k) s[k] = run_states[r * 32 + k];
+	uint32_t *fifo = fifo_s + t;
+	uint32_t pos = 32;                                   // FIFO read position (uniform); 32 = empty
+	uint32_t ch = 0, nb = 0;                             // carry: the top nb bytes of ch are the next undrawn draws (nb uniform)
 	const uint32_t C = L.C, full = C >> 2, rem = C & 3;
+	const uint32_t rmask = (1u << (8 * rem)) - 1u;
+	auto pop = [&]() -> uint32_t {
+		if (pos == 32) {
+			well_turn<0>(s, fifo);
+			pos = 0;
+		}
+		return fifo[(pos++) * QZ_THREADS];               // thread-private column: no barrier needed
+	};
 	for (uint32_t i = 0; i < L.Lr; ++i) {
 		uint32_t *dp = Dw + (uint64_t) i * L.T + r;
-		const uint32_t ph = (i * C) & 3;
-		switch (ph) {
-		case 0: for (uint32_t c4 = 0; c4 < full; ++c4) st_stream_u32(dp + (uint64_t) c4 * L.P, qz_draw_word<0>(q)); break;
-		case 1: for (uint32_t c4 = 0; c4 < full; ++c4) st_stream_u32(dp + (uint64_t) c4 * L.P, qz_draw_word<1>(q)); break;
-		case 2: for (uint32_t c4 = 0; c4 < full; ++c4) st_stream_u32(dp + (uint64_t) c4 * L.P, qz_draw_word<2>(q)); break;
-		default: for (uint32_t c4 = 0; c4 < full; ++c4) st_stream_u32(dp + (uint64_t) c4 * L.P, qz_draw_word<3>(q)); break;
+		const uint32_t sh = 32 - 8 * nb;                 // constant along a line: every full word takes 4 bytes and adds 4
+		for (uint32_t c4 = 0; c4 < full; ++c4) {
+			const uint32_t w = pop();
+			st_stream_u32(dp, __funnelshift_rc(ch, w, sh));
+			ch = w;
+			dp += L.P;
 		}
-		if (rem) {
-			uint32_t d = 0;
-			for (uint32_t j = 0; j < rem; ++j) {
-				if (((ph + j) & 3) == 0) qz_refill(q);
-				d |= (q.bits & 127u) << (8 * j);
-				q.bits >>= 7;
+		if (rem) {                                       // last, partial word of the line
+			uint32_t v;
+			if (nb >= rem) {
+				v = ch >> sh;
+				nb -= rem;
+			} else {
+				const uint32_t w = pop();
+				v = __funnelshift_rc(ch, w, sh);
+				ch = w;
+				nb += 4 - rem;
 			}
-			st_stream_u32(dp + (uint64_t) full * L.P, d);
+			st_stream_u32(dp, v & rmask);
 		}
 	}
 }
@@ -357,20 +405,38 @@ qvz_quantize_vmax_kernel(uint64_t entries, const uint32_t *__restrict__ W, const
 	if ((threadIdx.x & 31) == 0 && m) atomicMax(vmax, (int) m);
 }
 
-// full 72x72 tables -> one contiguous image per COLUMN: G[col] = { W box [K][A][A] words, ratio rows [K][A4] bytes }
+// full 72x72 tables -> one contiguous image per COLUMN: G[col] = entry[K][A][A] (see the format above)
 __global__ void __launch_bounds__(256)
-qvz_quantize_compact_kernel(uint32_t K, uint32_t C, uint32_t A, uint32_t A4, const uint32_t *__restrict__ W,
-                            const uint8_t *__restrict__ R, uint8_t *__restrict__ G)
+qvz_quantize_compact_kernel(uint32_t K, uint32_t C, uint32_t A, const uint32_t *__restrict__ W,
+                            const uint8_t *__restrict__ R, uint32_t *__restrict__ G)
 {
 	const uint64_t idx = (uint64_t) blockIdx.x * 256 + threadIdx.x;
 	if (idx >= (uint64_t) K * C * A * A) return;
 	const uint32_t x = idx % A, v = (idx / A) % A;
 	const uint64_t kc = idx / ((uint64_t) A * A);
 	const uint32_t k = kc / C, col = kc - (uint64_t) k * C;
-	const size_t col_bytes = (size_t) K * A * A * 4 + (size_t) K * A4;
-	uint8_t *g = G + col * col_bytes;
-	((uint32_t *) g)[((size_t) k * A + v) * A + x] = (x < 72 && v < 72) ? W[(kc * 72 + v) * 72 + x] : 0u;
-	if (x == 0) g[(size_t) K * A * A * 4 + (size_t) k * A4 + v] = v < 72 ? R[kc * 72 + v] : 0xFF;
+	uint32_t var[2];
+	if (R[kc * 72 + v] == 0xFF) {                    // no such context: poison
+		var[0] = (QB_POISON << 8) | (0x7Fu << 16);
+		var[1] = (QB_POISON << 8) | (0xFFu << 16);
+	} else {
+		const uint32_t e = W[(kc * 72 + v) * 72 + x];
+#pragma unroll
+		for (uint32_t hi = 0; hi < 2; ++hi) {
+			const uint32_t qv = (e >> (8 * hi)) & 0xFFu, st = (e >> (16 + 8 * hi)) & 0xFFu;
+			uint32_t nr = 0;
+			if (col + 1 < C) {
+				nr = R[(kc + 1) * 72 + qv];
+				if (nr == 0xFF) nr = 1;              // the poisoned row of the next column reports it
+			}
+			nr = (nr - 1u) & 0xFFu;
+			const uint32_t d = x > qv ? x - qv : qv - x;
+			var[hi] = qv | (d << 8) | (st << 16) | (nr << 24);
+		}
+	}
+	uint32_t *g = (uint32_t *) G + (size_t) col * 2 * K * A * A + ((size_t) k * A + v) * A + x;
+	g[0] = var[0];
+	g[(size_t) K * A * A] = var[1];
 }
 
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a): one elected thread moves a whole column-group image
@@ -396,30 +462,44 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, u
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+	double v;
+	asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
 
 // S = columns staged per barrier (4, 2 or 1: the largest whose double buffer fits shared memory)
 template <int DMODE, bool WANT_QV, int S>
 __global__ void __launch_bounds__(QB_THREADS, 1)
 qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint32_t *__restrict__ Dw,
                             const uint8_t *__restrict__ cl, const uint8_t *__restrict__ G,
-                            const double *__restrict__ D, uint32_t K,
-                            uint32_t A, uint32_t A4, uint32_t *__restrict__ Yw, uint32_t *__restrict__ Qw,
+                            const uint8_t *__restrict__ R, const double *__restrict__ D, uint32_t K,
+                            uint32_t A, uint32_t *__restrict__ Yw, uint32_t *__restrict__ Qw,
                             double *__restrict__ Ep, int *__restrict__ flags)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
-	// [dd: 72 doubles][2 mbarriers][buffer 0][buffer 1]; a buffer = S consecutive column images of G, each
-	// image = K*A*A table words followed by K*A4 ratio bytes
+	// [dd: 73 doubles (or 73 words)][2 mbarriers][buffer 0][buffer 1]; a buffer = S consecutive column images of G
+	constexpr uint32_t DD_WORDS = 2 * (QVZ_ALPHABET + 2);
 	double *dd = (double *) smem;
 	uint32_t *di = smem;
-	uint64_t *full = (uint64_t *) (smem + 2 * QVZ_ALPHABET);
-	const uint32_t tab_words = K * A * A;
-	const uint32_t col_bytes = tab_words * 4 + K * A4;     // multiple of 16
-	const uint32_t col_words = col_bytes / 4;
-	uint32_t *buf0 = smem + 2 * QVZ_ALPHABET + 4;
-	const uint32_t buf_words = S * col_words;
+	uint64_t *full = (uint64_t *) (smem + DD_WORDS);
+	const uint32_t col_bytes = K * A * A * 8;            // multiple of 32 (A is even)
+	const uint32_t buf_bytes = S * col_bytes;
+	const uint32_t buf0 = smem_u32(smem + DD_WORDS + 4);
+	const uint32_t dd_addr = smem_u32(smem);
 	const uint32_t tid = threadIdx.x;
-	if (DMODE == 1 && tid < QVZ_ALPHABET) dd[tid] = D[tid];
-	if (DMODE == 2 && tid < QVZ_ALPHABET) di[tid] = (uint32_t) D[tid];
+	if (DMODE == 1 && tid <= QVZ_ALPHABET) dd[tid] = tid < QVZ_ALPHABET ? D[tid] : __longlong_as_double(0x7FF8000000000000ll);
+	if (DMODE == 2 && tid <= QVZ_ALPHABET) di[tid] = tid < QVZ_ALPHABET ? (uint32_t) D[tid] : 0x80000000u;
 	if (tid == 0) {
 		mbar_init(&full[0], 1);
 		mbar_init(&full[1], 1);
@@ -428,20 +508,23 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 	__syncthreads();
 
 	const uint32_t C = L.C, C4 = L.C4;
+	const uint32_t A4 = A * 4;
+	const uint32_t plane = K * A * A4;                   // bytes from a lo variant to its hi variant
 	uint32_t gcount = 0;                             // column groups consumed so far (uniform): buffer = gcount & 1
 	auto stage = [&](uint32_t col0, uint32_t g) {    // thread 0: columns col0 .. min(col0+S, C)-1 -> buffer g & 1
 		const uint32_t ncol = (C - col0 < (uint32_t) S) ? C - col0 : (uint32_t) S;
 		const uint32_t bytes = ncol * col_bytes;
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this buffer are done
 		mbar_expect_tx(&full[g & 1], bytes);
-		tma_bulk_g2s(buf0 + (g & 1) * buf_words, G + (uint64_t) col0 * col_bytes, bytes, &full[g & 1]);
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		             ::"r"(buf0 + (g & 1) * buf_bytes), "l"(G + (uint64_t) col0 * col_bytes), "r"(bytes), "r"(smem_u32(&full[g & 1])) : "memory");
 	};
 
 	bool missing = false;
 	const uint64_t nbatch = L.P / QB_LINES;
 	for (uint64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
 		const uint64_t pbase = batch * QB_LINES + tid;   // line j of this thread: slot pbase + j*QB_THREADS
-		uint32_t koff[QB_LPT], roff[QB_LPT], prev[QB_LPT], maxr[QB_LPT], erri[QB_LPT];
+		uint32_t koff[QB_LPT], vprev[QB_LPT], erri[QB_LPT];
 		double errd[QB_LPT];
 		bool valid[QB_LPT];
 #pragma unroll
@@ -449,10 +532,9 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			const uint32_t kraw = cl[pbase + j * QB_THREADS];
 			valid[j] = kraw != QVZ_NO_LINE;
 			const uint32_t k = valid[j] ? kraw : 0;      // a slot without a line walks cluster 0's tables on zero data
-			koff[j] = k * A * A;
-			roff[j] = k * A4;
-			prev[j] = 0;
-			maxr[j] = 0;
+			koff[j] = k * A * A4;
+			// column 0: previous value 0 (src/qv_compressor.c:89), its ratio is the first byte of the cluster's R rows
+			vprev[j] = ((uint32_t) __ldg(R + (size_t) k * C * 72) - 1u) << 24;
 			erri[j] = 0;
 			errd[j] = 0.0;
 		}
@@ -463,7 +545,9 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			xn[j] = ld_stream_u32(Xw + pbase + j * QB_THREADS);
 			dn[j] = ld_stream_u32(Dw + pbase + j * QB_THREADS);
 		}
-		for (uint32_t c4 = 0; c4 < C4; ++c4) {
+		// one data word (4 columns) of the QB_LPT lines of this thread; TAIL = the last, partial word
+		auto word = [&](uint32_t c4, auto tail_tag) {
+			constexpr bool TAIL = decltype(tail_tag)::value;
 			uint32_t x[QB_LPT], dr[QB_LPT], outw[QB_LPT], qvw[QB_LPT];
 #pragma unroll
 			for (int j = 0; j < QB_LPT; ++j) {
@@ -472,7 +556,7 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 				outw[j] = 0;
 				qvw[j] = 0;
 			}
-			if (c4 + 1 < C4) {                           // next word's rows and draws: in flight during this word
+			if (!TAIL) {                                 // next word's rows and draws: in flight during this word
 				const uint32_t *xr = Xw + (uint64_t) (c4 + 1) * L.P + pbase, *drw = Dw + (uint64_t) (c4 + 1) * L.P + pbase;
 #pragma unroll
 				for (int j = 0; j < QB_LPT; ++j) {
@@ -481,33 +565,40 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 				}
 			}
 #pragma unroll
-			for (int b = 0; b < 4; ++b) {
-				const uint32_t col = 4 * c4 + b;
-				if (col < C) {
-					if ((b % S) == 0) {
-						__syncthreads();             // everyone is done with the previous group: its buffer is free
-						if (tid == 0 && col + S < C) stage(col + S, gcount + 1);
-						mbar_wait(&full[gcount & 1], (gcount >> 1) & 1);   // this group's image has landed
-					}
-					const uint32_t *tab = buf0 + (gcount & 1) * buf_words + (b % S) * col_words;
-					const uint8_t *rt = (const uint8_t *) (tab + tab_words);
+			for (int g = 0; g < 4 / S; ++g) {            // the column groups (= staged images) inside this word
+				const uint32_t col0 = 4 * c4 + g * S;
+				if (!TAIL || col0 < C) {
+					__syncthreads();                     // everyone is done with the previous group: its buffer is free
+					if (tid == 0 && col0 + S < C) stage(col0 + S, gcount + 1);
+					mbar_wait(&full[gcount & 1], (gcount >> 1) & 1);   // this group's image has landed
+					const uint32_t tabg = buf0 + (gcount & 1) * buf_bytes;
+					gcount += 1;
 #pragma unroll
-					for (int j = 0; j < QB_LPT; ++j) {
-						const uint32_t draw = __byte_perm(dr[j], 0, 0x4440 + b);
-						const uint32_t data = __byte_perm(x[j], 0, 0x4440 + b);
-						const uint32_t e = tab[koff[j] + prev[j] * A + data];
-						const uint32_t ratio = rt[roff[j] + prev[j]];
-						maxr[j] = max(maxr[j], ratio);
-						const uint32_t hi = draw >= ratio;
-						const uint32_t qv = __byte_perm(e, 0, 0x4440 + hi);
-						outw[j] = __byte_perm(outw[j], e, (0x3210 & ~(0xF << (4 * b))) + ((6 + hi) << (4 * b)));
-						if (WANT_QV) qvw[j] = __byte_perm(qvw[j], e, (0x3210 & ~(0xF << (4 * b))) + ((4 + hi) << (4 * b)));
-						if (DMODE == 2) erri[j] += di[abs((int) data - (int) qv)];
-						else if (DMODE == 1) errd[j] += dd[abs((int) data - (int) qv)];
-						else errd[j] += __ldg(&D[data + 72u * qv]);
-						prev[j] = qv;
+					for (int sidx = 0; sidx < S; ++sidx) {
+						const int b = g * S + sidx;
+						if (!TAIL || col0 + sidx < C) {
+							const uint32_t tab = tabg + sidx * col_bytes;
+#pragma unroll
+							for (int j = 0; j < QB_LPT; ++j) {
+								// draw >= qratio  <=>  (int)(draw << 24) > (int)((qratio-1) << 24 | low bits of the previous variant)
+								const int drawt = (int) __byte_perm(dr[j], 0, 0x0444 + (b << 12));
+								const uint32_t base = (drawt > (int) vprev[j]) ? tab + plane : tab;
+								const uint32_t data = __byte_perm(x[j], 0, 0x4440 + b);
+								const uint32_t row = (vprev[j] & 0x7Fu) * A4 + koff[j];
+								const uint32_t v = lds_u32(base + row + data * 4);
+								outw[j] = __byte_perm(outw[j], v, (0x3210 & ~(0xF << (4 * b))) + (6 << (4 * b)));
+								if (WANT_QV) qvw[j] = __byte_perm(qvw[j], v, (0x3210 & ~(0xF << (4 * b))) + (4 << (4 * b)));
+								const uint32_t didx = __byte_perm(v, 0, 0x4441);
+								if (DMODE == 2) erri[j] += lds_u32(dd_addr + didx * 4);
+								else if (DMODE == 1) errd[j] += lds_f64(dd_addr + didx * 8);
+								else {
+									if (didx == QB_POISON) missing |= valid[j];
+									errd[j] += __ldg(&D[data + 72u * (v & 0x7Fu)]);
+								}
+								vprev[j] = v;
+							}
+						}
 					}
-					if ((b % S) == S - 1 || col + 1 == C) gcount += 1;
 				}
 			}
 			uint32_t *yr = Yw + (uint64_t) c4 * L.P + pbase;
@@ -516,12 +607,15 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			if (WANT_QV) {
 				uint32_t *qr = Qw + (uint64_t) c4 * L.P + pbase;
 #pragma unroll
-				for (int j = 0; j < QB_LPT; ++j) st_stream_u32(qr + j * QB_THREADS, qvw[j] + 0x21212121u);
+				for (int j = 0; j < QB_LPT; ++j) st_stream_u32(qr + j * QB_THREADS, (qvw[j] & 0x7F7F7F7Fu) + 0x21212121u);
 			}
-		}
+		};
+		for (uint32_t c4 = 0; c4 + 1 < C4; ++c4) word(c4, std::false_type{});
+		word(C4 - 1, std::true_type{});
 #pragma unroll
 		for (int j = 0; j < QB_LPT; ++j) {
-			missing |= valid[j] && maxr[j] == 0xFFu;
+			if (DMODE == 2) missing |= valid[j] && erri[j] >= 0x80000000u;
+			if (DMODE == 1) missing |= valid[j] && errd[j] != errd[j];
 			Ep[pbase + j * QB_THREADS] = (DMODE == 2 ? (double) erri[j] : errd[j]) / (double) C;
 		}
 		__syncthreads();                             // the next batch restages into the other buffer's predecessor
@@ -529,14 +623,14 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 	if (missing) atomicOr(&flags[2], 1);
 }
 
-static size_t batched_smem(uint32_t K, uint32_t A, uint32_t A4, uint32_t S) {
-	return 2 * QVZ_ALPHABET * sizeof(uint32_t) + 16 + 2 * (size_t) S * ((size_t) K * A * A * 4 + (size_t) K * A4);
+static size_t batched_smem(uint32_t K, uint32_t A, uint32_t S) {
+	return 2 * (QVZ_ALPHABET + 2) * sizeof(uint32_t) + 16 + 2 * (size_t) S * ((size_t) K * A * A * 8);
 }
 
 // columns staged per barrier: the largest of 4, 2, 1 whose double buffer fits; 0 = batched path unusable
-uint32_t qvz_quantize_batched_group(uint32_t K, uint32_t A, uint32_t A4) {
+uint32_t qvz_quantize_batched_group(uint32_t K, uint32_t A) {
 	for (uint32_t S = 4; S >= 1; S >>= 1)
-		if (batched_smem(K, A, A4, S) <= 200 * 1024) return S;
+		if (batched_smem(K, A, S) <= 200 * 1024) return S;
 	return 0;
 }
 
@@ -555,42 +649,42 @@ int qvz_quantize_vmax(qvz_gpu *h, uint32_t KC, uint32_t smax) {
 	return QVZ_OK;
 }
 
-int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, uint32_t A4) {
+int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A) {
 	const uint64_t total = (uint64_t) K * C * A * A;
-	qvz_quantize_compact_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, h->stream>>>(K, C, A, A4, h->W, h->R, h->G);
+	qvz_quantize_compact_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, h->stream>>>(K, C, A, h->W, h->R, (uint32_t *) h->G);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;
 }
 
 template <int DMODE, bool WANT_QV, int S>
-static void launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t A4) {
+static void launch_batched(qvz_gpu *h, uint32_t K, uint32_t A) {
 	auto kern = qvz_quantize_batched_kernel<DMODE, WANT_QV, S>;
-	const size_t smem = batched_smem(K, A, A4, S);
+	const size_t smem = batched_smem(K, A, S);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	const uint64_t nbatch = h->L.P / QB_LINES;
 	const unsigned grid = (unsigned) (nbatch < (uint64_t) h->sm_count ? nbatch : (uint64_t) h->sm_count);
-	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->G, h->D, K, A, A4, h->Yw,
+	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->G, h->R, h->D, K, A, h->Yw,
 	                                            WANT_QV ? h->Qw : nullptr, h->Ep, h->flags);
 }
 
 template <int DMODE, bool WANT_QV>
-static void launch_batched_s(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t A4, uint32_t S) {
-	if (S == 4) launch_batched<DMODE, WANT_QV, 4>(h, K, A, A4);
-	else if (S == 2) launch_batched<DMODE, WANT_QV, 2>(h, K, A, A4);
-	else launch_batched<DMODE, WANT_QV, 1>(h, K, A, A4);
+static void launch_batched_s(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t S) {
+	if (S == 4) launch_batched<DMODE, WANT_QV, 4>(h, K, A);
+	else if (S == 2) launch_batched<DMODE, WANT_QV, 2>(h, K, A);
+	else launch_batched<DMODE, WANT_QV, 1>(h, K, A);
 }
 
-int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t A4, int want_qv, int dmode) {
-	const uint32_t S = qvz_quantize_batched_group(K, A, A4);
+int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, int want_qv, int dmode) {
+	const uint32_t S = qvz_quantize_batched_group(K, A);
 	if (want_qv) {
-		if (dmode == 2) launch_batched_s<2, true>(h, K, A, A4, S);
-		else if (dmode == 1) launch_batched_s<1, true>(h, K, A, A4, S);
-		else launch_batched_s<0, true>(h, K, A, A4, S);
+		if (dmode == 2) launch_batched_s<2, true>(h, K, A, S);
+		else if (dmode == 1) launch_batched_s<1, true>(h, K, A, S);
+		else launch_batched_s<0, true>(h, K, A, S);
 	} else {
-		if (dmode == 2) launch_batched_s<2, false>(h, K, A, A4, S);
-		else if (dmode == 1) launch_batched_s<1, false>(h, K, A, A4, S);
-		else launch_batched_s<0, false>(h, K, A, A4, S);
+		if (dmode == 2) launch_batched_s<2, false>(h, K, A, S);
+		else if (dmode == 1) launch_batched_s<1, false>(h, K, A, S);
+		else launch_batched_s<0, false>(h, K, A, S);
 	}
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());

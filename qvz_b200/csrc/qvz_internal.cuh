@@ -3,7 +3,7 @@
 // Device-resident data layout:
 //
 //   slot p  <->  line n :   the shard's lines are cut into T "runs" of Lr consecutive lines
-//                           (Lr % 4 == 0 so that every run starts on a WELL word boundary);
+//                           (Lr % 16 == 0: every run starts on a WELL word boundary and P % 4096 == 0);
 //                           run r, step i  =  line r*Lr + i  =  slot p = i*T + r.
 //                           Thread r of the quantize kernel walks run r sequentially, so its WELL1024a
 //                           stream is one contiguous piece of the reference's draw stream, while
@@ -20,7 +20,7 @@
 #include "../../include/qvz_gpu.h"
 
 #define QVZ_THREADS 256
-#define QVZ_RUN_ALIGN 1024    // runs per shard are a multiple of this (batched quantize: 1024 threads x 4 lines)
+#define QVZ_RUN_ALIGN 256     // runs per shard are a multiple of this (one CTA of the draw generator); Lr % 16 == 0 => P % 4096 == 0
 #define QVZ_NFLAGS 8
 #define QVZ_NO_LINE 0xFFu
 #define QVZ_MAX_K 16            // register-resident distances in the k-means kernel
@@ -30,7 +30,7 @@ struct qvz_layout {
 	uint64_t first_line; // global index of line 0 of the shard
 	uint32_t C;          // columns
 	uint32_t C4;         // ceil(C/4) words per line
-	uint32_t Lr;         // lines per run (multiple of 4)
+	uint32_t Lr;         // lines per run (multiple of 16)
 	uint32_t T;          // runs (multiple of QVZ_THREADS)
 	uint64_t P;          // slots = T * Lr
 };
@@ -76,7 +76,7 @@ struct qvz_gpu {
 	uint32_t *run_states;    // [T][32] WELL state (n = 0 frame) at the first draw of each run
 	uint32_t *Yw, *Qw;       // [C4][P] packed outputs (state|hi<<7, qv+33)
 	uint32_t *Dw;            // [C4][P] packed 7-bit WELL draws, one byte per (line, column)
-	uint8_t *G;              // compact tables, one image per column: { W box [K][A][A] u32, ratios [K][A4] u8 }
+	uint8_t *G;              // compact tables, one image per column: entry[K][A][A] of 8 bytes (quantize.cu)
 	size_t G_cap;
 	uint32_t smax;           // largest symbol value in the resident rows
 	double *Ep;              // [P] per-slot error / C
@@ -130,8 +130,8 @@ int qvz_well_jump_state(qvz_gpu *h, const uint32_t seed[32], uint64_t words, uin
 int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int toeplitz);
 int qvz_quantize_draws(qvz_gpu *h);
 int qvz_quantize_vmax(qvz_gpu *h, uint32_t KC, uint32_t smax);
-int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, uint32_t A4);
-uint32_t qvz_quantize_batched_group(uint32_t K, uint32_t A, uint32_t A4);
-int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t A4, int want_qv, int dmode);
+int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A);
+uint32_t qvz_quantize_batched_group(uint32_t K, uint32_t A);
+int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, int want_qv, int dmode);
 int qvz_quantize_compose(qvz_gpu *h, uint32_t KC, const uint32_t *nctx, const uint8_t *ctx_of, const uint64_t *q_off,
                          const uint8_t *qratio, const uint8_t *qmap, const uint8_t *smap);

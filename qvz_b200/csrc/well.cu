@@ -25,11 +25,13 @@
 
 struct qvz_well_cache {
 	std::vector<uint32_t *> pow2;     // column forms of A^(2^j)
+	std::vector<uint32_t *> pow2_tabs; // their byte tables, built on first use by a vector jump (nullptr = not yet)
 	uint32_t *tab;                    // scratch byte table, 4 MiB
 	uint32_t *tmp_a, *tmp_b;          // scratch column forms
 	uint32_t *vec_a, *vec_b;          // scratch single vectors
 	uint64_t lw;                      // words per run the levels below were built for
 	std::vector<uint32_t *> levels;   // column forms of M_b
+	std::vector<uint32_t *> level_tabs; // byte tables of M_b (4 MiB each), kept so that a quantize call only applies them
 };
 
 // host: one step in the rotated frame (restates src/well.c:8-24 with n folded away)
@@ -75,17 +77,17 @@ qvz_f2_apply_kernel(const uint32_t *__restrict__ tab, const uint32_t *__restrict
 	out[(uint64_t) v * 32 + lane] = acc;
 }
 
-static int f2_table(qvz_gpu *h, const uint32_t *Mc) {
-	qvz_f2_build_table_kernel<<<128, 32, 0, h->stream>>>(Mc, h->well->tab);
+static int f2_table(qvz_gpu *h, const uint32_t *Mc, uint32_t *tab = nullptr) {
+	qvz_f2_build_table_kernel<<<128, 32, 0, h->stream>>>(Mc, tab ? tab : h->well->tab);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;
 }
 
-static int f2_apply(qvz_gpu *h, const uint32_t *in, uint32_t *out, uint32_t count) {
+static int f2_apply(qvz_gpu *h, const uint32_t *in, uint32_t *out, uint32_t count, const uint32_t *tab = nullptr) {
 	if (!count) return QVZ_OK;
 	const unsigned grid = (count * 32 + QVZ_THREADS - 1) / QVZ_THREADS;
-	qvz_f2_apply_kernel<<<grid, QVZ_THREADS, 0, h->stream>>>(h->well->tab, in, out, count);
+	qvz_f2_apply_kernel<<<grid, QVZ_THREADS, 0, h->stream>>>(tab ? tab : h->well->tab, in, out, count);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;
@@ -122,7 +124,9 @@ void qvz_well_free(qvz_gpu *h) {
 	qvz_well_cache *w = h->well;
 	if (!w) return;
 	for (uint32_t *p : w->pow2) cudaFree(p);
+	for (uint32_t *p : w->pow2_tabs) cudaFree(p);
 	for (uint32_t *p : w->levels) cudaFree(p);
+	for (uint32_t *p : w->level_tabs) cudaFree(p);
 	cudaFree(w->tab);
 	cudaFree(w->tmp_a);
 	cudaFree(w->tmp_b);
@@ -157,9 +161,13 @@ static int jump_vector(qvz_gpu *h, uint64_t e, uint32_t *vec /* = w->vec_a */) {
 		if (!((e >> j) & 1)) continue;
 		int rc = ensure_pow2(h, j);
 		if (rc) return rc;
-		rc = f2_table(h, w->pow2[j]);
-		if (rc) return rc;
-		rc = f2_apply(h, cur, other, 1);
+		if (w->pow2_tabs.size() <= j) w->pow2_tabs.resize(j + 1, nullptr);
+		if (!w->pow2_tabs[j]) {
+			QVZ_CUDA(h, cudaMalloc(&w->pow2_tabs[j], (size_t) WELL_TAB_WORDS * sizeof(uint32_t)));
+			rc = f2_table(h, w->pow2[j], w->pow2_tabs[j]);
+			if (rc) return rc;
+		}
+		rc = f2_apply(h, cur, other, 1, w->pow2_tabs[j]);
 		if (rc) return rc;
 		uint32_t *t = cur;
 		cur = other;
@@ -185,7 +193,9 @@ static int ensure_levels(qvz_gpu *h, uint64_t lw, uint32_t nlevels) {
 	const size_t msz = (size_t) WELL_BITS * WELL_WORDS * sizeof(uint32_t);
 	if (w->lw != lw) {
 		for (uint32_t *p : w->levels) cudaFree(p);
+		for (uint32_t *p : w->level_tabs) cudaFree(p);
 		w->levels.clear();
+		w->level_tabs.clear();
 		w->lw = lw;
 	}
 	if (w->levels.empty() && nlevels) {
@@ -222,6 +232,13 @@ static int ensure_levels(qvz_gpu *h, uint64_t lw, uint32_t nlevels) {
 		if (rc) return rc;
 		w->levels.push_back(next);
 	}
+	while (w->level_tabs.size() < nlevels) {
+		uint32_t *tab = nullptr;
+		QVZ_CUDA(h, cudaMalloc(&tab, (size_t) WELL_TAB_WORDS * sizeof(uint32_t)));
+		w->level_tabs.push_back(tab);
+		int rc = f2_table(h, w->levels[w->level_tabs.size() - 1], tab);
+		if (rc) return rc;
+	}
 	return QVZ_OK;
 }
 
@@ -240,9 +257,7 @@ int qvz_well_run_states(qvz_gpu *h, const uint32_t seed[32]) {
 	for (uint32_t b = 0; b < nlevels; ++b) {
 		const uint64_t have = 1ull << b;
 		const uint64_t todo = (L.T - have < have) ? L.T - have : have;
-		rc = f2_table(h, h->well->levels[b]);
-		if (rc) return rc;
-		rc = f2_apply(h, h->run_states, h->run_states + have * WELL_WORDS, (uint32_t) todo);
+		rc = f2_apply(h, h->run_states, h->run_states + have * WELL_WORDS, (uint32_t) todo, h->well->level_tabs[b]);
 		if (rc) return rc;
 	}
 	return QVZ_OK;
