@@ -17,14 +17,132 @@ static void free_dev(void *p) {
 }
 
 static void release_rows(qvz_gpu *h) {
-	free_dev(h->Xw); h->Xw = nullptr;
-	free_dev(h->cl); h->cl = nullptr;
-	free_dev(h->run_states); h->run_states = nullptr;
-	free_dev(h->Yw); h->Yw = nullptr;
-	free_dev(h->Qw); h->Qw = nullptr;
-	free_dev(h->Ep); h->Ep = nullptr;
-	free_dev(h->Dw); h->Dw = nullptr;
+	free_dev(h->Xw); h->Xw = nullptr; h->Xw_cap = 0;
+	free_dev(h->cl); h->cl = nullptr; h->cl_cap = 0;
+	free_dev(h->run_states); h->run_states = nullptr; h->rs_cap = 0;
+	free_dev(h->Yw); h->Yw = nullptr; h->Yw_cap = 0;
+	free_dev(h->Qw); h->Qw = nullptr; h->Qw_cap = 0;
+	free_dev(h->Ep); h->Ep = nullptr; h->Ep_cap = 0;
+	free_dev(h->Dw); h->Dw = nullptr; h->Dw_cap = 0;
 	h->K = 0;
+}
+
+// grow-only device buffer: repeated calls on same-shaped inputs never touch the allocator
+template <class T>
+static int ensure_buf(qvz_gpu *h, T **p, size_t *cap, size_t bytes) {
+	if (*p && *cap >= bytes) return QVZ_OK;
+	free_dev(*p);
+	*p = nullptr;
+	*cap = 0;
+	QVZ_CUDA(h, cudaMalloc(p, bytes));
+	*cap = bytes;
+	return QVZ_OK;
+}
+
+// ---- host <-> device pipeline ---------------------------------------------------------------------------
+// The host side of every transfer is line-major, the device side is the packed slot layout, and a range of
+// whole runs is a contiguous range of lines (layout.cu).  So a transfer is cut into pieces of whole runs that
+// fit one of two staging buffers; piece k crosses PCIe on the copy stream while piece k-1 is re-laid out on
+// the compute stream.  Events order the two streams per buffer; nothing blocks the host until the end.
+#define QVZ_STAGE_BYTES ((size_t) 64 << 20)
+
+static int ensure_stage(qvz_gpu *h, size_t min_bytes) {
+	size_t want = QVZ_STAGE_BYTES > min_bytes ? QVZ_STAGE_BYTES : min_bytes;
+	if (h->stage[0] && h->stage_bytes >= want) return QVZ_OK;
+	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+	QVZ_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+	for (int b = 0; b < 2; ++b) {
+		free_dev(h->stage[b]);
+		h->stage[b] = nullptr;
+		QVZ_CUDA(h, cudaMalloc(&h->stage[b], want));
+	}
+	h->stage_bytes = want;
+	return QVZ_OK;
+}
+
+struct piece {
+	uint32_t r0, nr;         // runs
+	uint64_t l0, l1;         // lines [l0, l1) that exist in this piece (l0 == l1: padding runs only)
+	int buf;
+};
+
+// pieces of whole runs whose line-major image (row pitch `stride`) fits a staging buffer
+static int plan_pieces(qvz_gpu *h, size_t stride, uint32_t *runs_per_piece) {
+	const qvz_layout &L = h->L;
+	const size_t per_run = (size_t) L.Lr * stride;
+	int rc = ensure_stage(h, per_run);
+	if (rc) return rc;
+	uint64_t n = h->stage_bytes / per_run;
+	if (n >= 64) n &= ~(uint64_t) 31;            // whole warps of runs: coalesced on the packed side
+	if (n > L.T) n = L.T;
+	*runs_per_piece = (uint32_t) n;
+	return QVZ_OK;
+}
+
+static piece make_piece(const qvz_gpu *h, uint32_t r0, uint32_t per, int k) {
+	const qvz_layout &L = h->L;
+	piece pc;
+	pc.r0 = r0;
+	pc.nr = (L.T - r0 < per) ? L.T - r0 : per;
+	pc.l0 = (uint64_t) r0 * L.Lr;
+	pc.l1 = (uint64_t) (r0 + pc.nr) * L.Lr;
+	if (pc.l0 > L.n_lines) pc.l0 = L.n_lines;
+	if (pc.l1 > L.n_lines) pc.l1 = L.n_lines;
+	pc.buf = k & 1;
+	return pc;
+}
+
+// host -> device.  consume(piece, staged bytes) launches the re-layout kernel on h->stream.
+template <class F>
+static int pipeline_h2d(qvz_gpu *h, const uint8_t *host, size_t stride, size_t row_bytes, F consume) {
+	uint32_t per = 0;
+	int rc = plan_pieces(h, stride, &per);
+	if (rc) return rc;
+	bool used[2] = {false, false};
+	int k = 0;
+	for (uint32_t r0 = 0; r0 < h->L.T; r0 += per, ++k) {
+		const piece pc = make_piece(h, r0, per, k);
+		if (pc.l1 > pc.l0) {
+			const size_t bytes = (size_t) (pc.l1 - pc.l0 - 1) * stride + row_bytes;
+			if (used[pc.buf]) QVZ_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[pc.buf], 0));
+			QVZ_CUDA(h, cudaMemcpyAsync(h->stage[pc.buf], host + (size_t) pc.l0 * stride, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+			QVZ_CUDA(h, cudaEventRecord(h->ev_copied[pc.buf], h->copy_stream));
+			QVZ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_copied[pc.buf], 0));
+		}
+		rc = consume(pc);
+		if (rc) return rc;
+		if (pc.l1 > pc.l0) {
+			QVZ_CUDA(h, cudaEventRecord(h->ev_consumed[pc.buf], h->stream));
+			used[pc.buf] = true;
+		}
+	}
+	return QVZ_OK;
+}
+
+// device -> host.  produce(piece) launches the re-layout kernel on h->stream, writing stage[piece.buf].
+template <class F>
+static int pipeline_d2h(qvz_gpu *h, uint8_t *host, size_t stride, size_t row_bytes, F produce) {
+	uint32_t per = 0;
+	int rc = plan_pieces(h, stride, &per);
+	if (rc) return rc;
+	bool used[2] = {false, false};
+	int k = 0;
+	for (uint32_t r0 = 0; r0 < h->L.T; r0 += per, ++k) {
+		const piece pc = make_piece(h, r0, per, k);
+		if (pc.l1 == pc.l0) break;               // only padding runs from here on
+		if (used[pc.buf]) QVZ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_consumed[pc.buf], 0));
+		rc = produce(pc);
+		if (rc) return rc;
+		QVZ_CUDA(h, cudaEventRecord(h->ev_copied[pc.buf], h->stream));
+		QVZ_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copied[pc.buf], 0));
+		const size_t bytes = (size_t) (pc.l1 - pc.l0 - 1) * stride + row_bytes;
+		QVZ_CUDA(h, cudaMemcpyAsync(host + (size_t) pc.l0 * stride, h->stage[pc.buf], bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+		QVZ_CUDA(h, cudaEventRecord(h->ev_consumed[pc.buf], h->copy_stream));
+		used[pc.buf] = true;
+	}
+	QVZ_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+	return QVZ_OK;
 }
 
 static void release_kmeans(qvz_gpu *h) {
@@ -33,6 +151,8 @@ static void release_kmeans(qvz_gpu *h) {
 	free_dev(h->means_sq); h->means_sq = nullptr;
 	free_dev(h->sums); h->sums = nullptr;
 	free_dev(h->moved); h->moved = nullptr;
+	free_dev(h->counts_dev); h->counts_dev = nullptr;
+	h->means_b_cap = h->means_w_cap = h->means_sq_cap = h->sums_cap = h->moved_cap = h->counts_cap = 0;
 	if (h->h_moved) cudaFreeHost(h->h_moved);
 	if (h->h_counts) cudaFreeHost(h->h_counts);
 	h->h_moved = nullptr;
@@ -71,7 +191,12 @@ extern "C" int qvz_gpu_open(qvz_gpu **out, int device) {
 	QVZ_CUDA(h, cudaSetDevice(device));
 	QVZ_CUDA(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
 	QVZ_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	QVZ_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 8; ++i) QVZ_CUDA(h, cudaEventCreate(&h->ev[i]));
+	for (int b = 0; b < 2; ++b) {
+		QVZ_CUDA(h, cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
+		QVZ_CUDA(h, cudaEventCreateWithFlags(&h->ev_consumed[b], cudaEventDisableTiming));
+	}
 	QVZ_CUDA(h, cudaMalloc(&h->flags, QVZ_NFLAGS * sizeof(int)));
 	QVZ_CUDA(h, cudaMemsetAsync(h->flags, 0, QVZ_NFLAGS * sizeof(int), h->stream));
 	QVZ_CUDA(h, cudaMallocHost(&h->h_flags, QVZ_NFLAGS * sizeof(int)));
@@ -83,7 +208,14 @@ extern "C" void qvz_gpu_close(qvz_gpu *h) {
 	if (!h) return;
 	cudaSetDevice(h->device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
+	if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
 	release_rows(h);
+	for (int b = 0; b < 2; ++b) {
+		free_dev(h->stage[b]);
+		if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
+		if (h->ev_consumed[b]) cudaEventDestroy(h->ev_consumed[b]);
+	}
+	if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
 	release_kmeans(h);
 	qvz_well_free(h);
 	free_dev(h->W);
@@ -127,7 +259,7 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 		QVZ_FAIL(h, QVZ_ERR_ARG, "load_rows: need n_lines > 0, 0 < columns <= %u, row_stride >= columns", QVZ_MAX_COLUMNS);
 	if (first_line & 3) QVZ_FAIL(h, QVZ_ERR_ARG, "load_rows: first_line must be a multiple of 4");
 	QVZ_CUDA(h, cudaSetDevice(h->device));
-	release_rows(h);
+	h->K = 0;                                    // the resident cluster ids belong to the previous rows
 
 	qvz_layout &L = h->L;
 	L.n_lines = n_lines;
@@ -144,28 +276,27 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 	L.T = (uint32_t) ((runs + QVZ_RUN_ALIGN - 1) / QVZ_RUN_ALIGN * QVZ_RUN_ALIGN);
 	L.P = (uint64_t) L.T * L.Lr;
 
-	uint8_t *raw = nullptr;
-	const size_t raw_bytes = (size_t) ((n_lines - 1) * (uint64_t) row_stride + columns);
-	QVZ_CUDA(h, cudaMalloc(&raw, raw_bytes));
-	QVZ_CUDA(h, cudaMalloc(&h->Xw, (size_t) L.C4 * L.P * sizeof(uint32_t)));
-	QVZ_CUDA(h, cudaMalloc(&h->cl, (size_t) L.P));
+	int rc = ensure_buf(h, &h->Xw, &h->Xw_cap, (size_t) L.C4 * L.P * sizeof(uint32_t));
+	if (rc) return rc;
+	rc = ensure_buf(h, &h->cl, &h->cl_cap, (size_t) L.P);
+	if (rc) return rc;
 	QVZ_CUDA(h, cudaMemsetAsync(h->flags + 5, 0, sizeof(int), h->stream));
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
-	QVZ_CUDA(h, cudaMemcpyAsync(raw, rows, raw_bytes, cudaMemcpyHostToDevice, h->stream));
-	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
-	int rc = qvz_layout_ingest(h, raw, row_stride);
-	if (rc) {
-		cudaFree(raw);
-		return rc;
-	}
-	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));
-	int bad = 0;
-	rc = take_flag(h, 0, &bad);
-	cudaFree(raw);
+	QVZ_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev[EV_A], 0));
+	rc = pipeline_h2d(h, rows, row_stride, columns, [&](const piece &pc) {
+		return qvz_layout_ingest(h, pc.r0, pc.nr, h->stage[pc.buf], row_stride);
+	});
 	if (rc) return rc;
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->copy_stream));      // the last byte has crossed PCIe
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));           // ... and has been packed
+	int bad = 0;
+	rc = take_flag(h, 0, &bad);                  // synchronises the compute stream
+	if (rc) return rc;
+	QVZ_CUDA(h, cudaStreamSynchronize(h->copy_stream));
 	h->smax = (uint32_t) h->h_flags[5];             // take_flag copied all flags back
 	h->tm.load_h2d_ms = ev_ms(h, EV_A, EV_B);
-	h->tm.load_layout_ms = ev_ms(h, EV_B, EV_C);
+	h->tm.load_layout_ms = ev_ms(h, EV_B, EV_C);    // re-layout time NOT hidden behind the copy
+	if (h->tm.load_layout_ms < 0.f) h->tm.load_layout_ms = 0.f;
 	if (bad) {
 		release_rows(h);
 		QVZ_FAIL(h, QVZ_ERR_SYMBOL_RANGE, "load_rows: a quality byte is outside ['!', '!'+71]");
@@ -179,16 +310,16 @@ extern "C" int qvz_gpu_kmeans_begin(qvz_gpu *h, uint32_t K, const uint8_t *init_
 	if (!h->Xw) QVZ_FAIL(h, QVZ_ERR_ARG, "kmeans: no rows loaded");
 	if (K == 0 || K > QVZ_MAX_K) QVZ_FAIL(h, QVZ_ERR_UNSUPPORTED, "kmeans: 1 <= clusters <= %d supported", QVZ_MAX_K);
 	QVZ_CUDA(h, cudaSetDevice(h->device));
-	release_kmeans(h);
 	const uint32_t C = h->L.C, C4 = h->L.C4;
 	h->km_K = K;
-	QVZ_CUDA(h, cudaMalloc(&h->means_b, (size_t) K * C));
-	QVZ_CUDA(h, cudaMalloc(&h->means_w, (size_t) K * C4 * sizeof(uint32_t)));
-	QVZ_CUDA(h, cudaMalloc(&h->means_sq, K * sizeof(uint32_t)));
-	QVZ_CUDA(h, cudaMalloc(&h->sums, ((size_t) K * C + K) * sizeof(int64_t)));
-	QVZ_CUDA(h, cudaMalloc(&h->moved, K * sizeof(double)));
-	QVZ_CUDA(h, cudaMallocHost(&h->h_moved, K * sizeof(double)));
-	QVZ_CUDA(h, cudaMallocHost(&h->h_counts, K * sizeof(uint32_t)));
+	int rc = ensure_buf(h, &h->means_b, &h->means_b_cap, (size_t) K * C);
+	if (!rc) rc = ensure_buf(h, &h->means_w, &h->means_w_cap, (size_t) K * C4 * sizeof(uint32_t));
+	if (!rc) rc = ensure_buf(h, &h->means_sq, &h->means_sq_cap, K * sizeof(uint32_t));
+	if (!rc) rc = ensure_buf(h, &h->sums, &h->sums_cap, ((size_t) K * C + K) * sizeof(int64_t));
+	if (!rc) rc = ensure_buf(h, &h->moved, &h->moved_cap, K * sizeof(double));
+	if (rc) return rc;
+	if (!h->h_moved) QVZ_CUDA(h, cudaMallocHost(&h->h_moved, QVZ_MAX_K * sizeof(double)));
+	if (!h->h_counts) QVZ_CUDA(h, cudaMallocHost(&h->h_counts, QVZ_MAX_K * sizeof(int64_t)));
 	QVZ_CUDA(h, cudaMemcpyAsync(h->means_b, init_means, (size_t) K * C, cudaMemcpyHostToDevice, h->stream));
 	h->K = K;
 	return qvz_kmeans_launch_update(h, nullptr);     // pack the initial centroids
@@ -206,9 +337,9 @@ extern "C" int qvz_gpu_kmeans_update_dev(qvz_gpu *h, const int64_t *sums_dev, do
 	const uint32_t K = h->km_K, C = h->L.C;
 	int rc = qvz_kmeans_launch_update(h, sums_dev);
 	if (rc) return rc;
-	std::vector<int64_t> cnt(K);
+	int64_t *cnt = (int64_t *) h->h_counts;
 	QVZ_CUDA(h, cudaMemcpyAsync(h->h_moved, h->moved, K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-	QVZ_CUDA(h, cudaMemcpyAsync(cnt.data(), sums_dev + (size_t) K * C, K * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(cnt, sums_dev + (size_t) K * C, K * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
 	int empty = 0;
 	rc = take_flag(h, 1, &empty);                    // synchronises the stream
 	if (rc) return rc;
@@ -221,19 +352,9 @@ extern "C" int qvz_gpu_kmeans_update_dev(qvz_gpu *h, const int64_t *sums_dev, do
 }
 
 static int ids_to_host(qvz_gpu *h, uint8_t *ids_out) {
-	uint8_t *ids_dev = nullptr;
-	QVZ_CUDA(h, cudaMalloc(&ids_dev, (size_t) h->L.n_lines));
-	int rc = qvz_layout_ids_to_lines(h, ids_dev);
-	if (!rc) {
-		cudaError_t e = cudaMemcpyAsync(ids_out, ids_dev, (size_t) h->L.n_lines, cudaMemcpyDeviceToHost, h->stream);
-		if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-		if (e != cudaSuccess) {
-			snprintf(h->err, sizeof(h->err), "ids D2H: %s", cudaGetErrorString(e));
-			rc = QVZ_ERR_CUDA;
-		}
-	}
-	cudaFree(ids_dev);
-	return rc;
+	return pipeline_d2h(h, ids_out, 1, 1, [&](const piece &pc) {
+		return qvz_layout_ids_to_lines(h, pc.r0, pc.nr, h->stage[pc.buf]);
+	});
 }
 
 extern "C" int qvz_gpu_kmeans_end(qvz_gpu *h, uint8_t *cluster_ids_out, uint8_t *means_out) {
@@ -289,16 +410,13 @@ extern "C" int qvz_gpu_set_clusters(qvz_gpu *h, uint32_t K, const uint8_t *clust
 	if (!h->Xw) QVZ_FAIL(h, QVZ_ERR_ARG, "set_clusters: no rows loaded");
 	if (K == 0 || K > 255) QVZ_FAIL(h, QVZ_ERR_ARG, "set_clusters: bad cluster count");
 	QVZ_CUDA(h, cudaSetDevice(h->device));
-	uint8_t *ids_dev = nullptr;
-	QVZ_CUDA(h, cudaMalloc(&ids_dev, (size_t) h->L.n_lines));
-	cudaError_t e = cudaMemcpyAsync(ids_dev, cluster_ids, (size_t) h->L.n_lines, cudaMemcpyHostToDevice, h->stream);
-	int rc = QVZ_OK;
-	if (e == cudaSuccess) rc = qvz_layout_ids_from_lines(h, ids_dev);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-	cudaFree(ids_dev);
-	if (e != cudaSuccess) QVZ_FAIL(h, QVZ_ERR_CUDA, "set_clusters: %s", cudaGetErrorString(e));
-	if (!rc) h->K = K;
-	return rc;
+	int rc = pipeline_h2d(h, cluster_ids, 1, 1, [&](const piece &pc) {
+		return qvz_layout_ids_from_lines(h, pc.r0, pc.nr, h->stage[pc.buf]);
+	});
+	if (rc) return rc;
+	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+	h->K = K;
+	return QVZ_OK;
 }
 
 // ------------------------------------------------------------------------------------------ counts
@@ -320,18 +438,13 @@ extern "C" int qvz_gpu_cond_counts(qvz_gpu *h, uint32_t *counts_out) {
 	if (!h->Xw || !h->K) QVZ_FAIL(h, QVZ_ERR_ARG, "cond_counts: rows and cluster ids must be resident first");
 	QVZ_CUDA(h, cudaSetDevice(h->device));
 	const size_t bytes = (size_t) qvz_gpu_cond_counts_len(h->K, h->L.C) * sizeof(uint32_t);
-	uint32_t *dev = nullptr;
-	QVZ_CUDA(h, cudaMalloc(&dev, bytes));
-	int rc = qvz_gpu_cond_counts_dev(h, dev);
+	int rc = ensure_buf(h, &h->counts_dev, &h->counts_cap, bytes);
+	if (rc) return rc;
+	rc = qvz_gpu_cond_counts_dev(h, h->counts_dev);
 	if (!rc && counts_out) {
-		cudaError_t e = cudaMemcpyAsync(counts_out, dev, bytes, cudaMemcpyDeviceToHost, h->stream);
-		if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-		if (e != cudaSuccess) {
-			snprintf(h->err, sizeof(h->err), "cond_counts D2H: %s", cudaGetErrorString(e));
-			rc = QVZ_ERR_CUDA;
-		}
+		QVZ_CUDA(h, cudaMemcpyAsync(counts_out, h->counts_dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+		QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
 	}
-	cudaFree(dev);
 	return rc;
 }
 
@@ -406,17 +519,19 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	QVZ_CUDA(h, cudaSetDevice(h->device));
 	const qvz_layout &L = h->L;
 	const size_t wbytes = (size_t) L.C4 * L.P * sizeof(uint32_t);
-	if (!h->Yw) QVZ_CUDA(h, cudaMalloc(&h->Yw, wbytes));
-	if (qv_out && !h->Qw) QVZ_CUDA(h, cudaMalloc(&h->Qw, wbytes));
-	if (!h->Ep) QVZ_CUDA(h, cudaMalloc(&h->Ep, (size_t) L.P * sizeof(double)));   // the walk always sums the distortion, like the reference
-	if (!h->run_states) QVZ_CUDA(h, cudaMalloc(&h->run_states, (size_t) L.T * 32 * sizeof(uint32_t)));
+	int rc = ensure_buf(h, &h->Yw, &h->Yw_cap, wbytes);
+	if (!rc && qv_out) rc = ensure_buf(h, &h->Qw, &h->Qw_cap, wbytes);
+	if (!rc) rc = ensure_buf(h, &h->Ep, &h->Ep_cap, (size_t) L.P * sizeof(double));   // the walk always sums the distortion, like the reference
+	if (!rc) rc = ensure_buf(h, &h->run_states, &h->rs_cap, (size_t) L.T * 32 * sizeof(uint32_t));
+	if (rc) return rc;
 
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
 	int toeplitz = 0;
-	int rc = upload_tables(h, t, &toeplitz);
+	rc = upload_tables(h, t, &toeplitz);
 	if (rc) return rc;
 	rc = qvz_well_run_states(h, well_seed);
 	if (rc) return rc;
+	qvz_well_debug(h, "after run_states");
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
 	// Fast path: compact the tables to the A x A box of values that can occur and walk column-synchronously
 	// from shared memory (quantize.cu).  A-1 = max(largest symbol in the rows, largest reachable quantized value).
@@ -441,7 +556,8 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 				QVZ_CUDA(h, cudaMalloc(&h->G, gbytes));
 				h->G_cap = gbytes;
 			}
-			if (!h->Dw) QVZ_CUDA(h, cudaMalloc(&h->Dw, wbytes));
+			rc = ensure_buf(h, &h->Dw, &h->Dw_cap, wbytes);
+			if (rc) return rc;
 			rc = qvz_quantize_compact(h, t->clusters, t->columns, A);
 			if (rc) return rc;
 		}
@@ -459,36 +575,26 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	if (rc) return rc;
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));
 
-	// egress: packed -> line-major on the device, then D2H
-	uint8_t *out_dev = nullptr;
-	double *err_dev = nullptr;
-	cudaError_t e = cudaSuccess;
+	// egress: packed -> line-major pieces on the device, each copied to the host while the next is re-laid out
 	if (symbols_out) {
-		const size_t bytes = (size_t) L.n_lines * L.C;
-		QVZ_CUDA(h, cudaMalloc(&out_dev, bytes));
-		rc = qvz_layout_words_to_lines(h, h->Yw, out_dev, L.C, 0);
-		if (!rc) e = cudaMemcpyAsync(symbols_out, out_dev, bytes, cudaMemcpyDeviceToHost, h->stream);
-		if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-		cudaFree(out_dev);
-		out_dev = nullptr;
+		rc = pipeline_d2h(h, symbols_out, L.C, L.C, [&](const piece &pc) {
+			return qvz_layout_words_to_lines(h, pc.r0, pc.nr, h->Yw, h->stage[pc.buf], L.C, 0);
+		});
+		if (rc) return rc;
 	}
-	if (!rc && e == cudaSuccess && qv_out) {
-		const size_t bytes = (size_t) L.n_lines * (L.C + 1);
-		e = cudaMalloc(&out_dev, bytes);
-		if (e == cudaSuccess) rc = qvz_layout_words_to_lines(h, h->Qw, out_dev, L.C + 1, 1);
-		if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(qv_out, out_dev, bytes, cudaMemcpyDeviceToHost, h->stream);
-		if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-		if (out_dev) cudaFree(out_dev);
+	if (qv_out) {
+		rc = pipeline_d2h(h, qv_out, L.C + 1, L.C + 1, [&](const piece &pc) {
+			return qvz_layout_words_to_lines(h, pc.r0, pc.nr, h->Qw, h->stage[pc.buf], L.C + 1, 1);
+		});
+		if (rc) return rc;
 	}
-	if (!rc && e == cudaSuccess && line_err_out) {
-		e = cudaMalloc(&err_dev, (size_t) L.n_lines * sizeof(double));
-		if (e == cudaSuccess) rc = qvz_layout_doubles_to_lines(h, h->Ep, err_dev);
-		if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(line_err_out, err_dev, (size_t) L.n_lines * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-		if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-		if (err_dev) cudaFree(err_dev);
+	if (line_err_out) {
+		rc = pipeline_d2h(h, (uint8_t *) line_err_out, sizeof(double), sizeof(double), [&](const piece &pc) {
+			return qvz_layout_doubles_to_lines(h, pc.r0, pc.nr, h->Ep, (double *) h->stage[pc.buf]);
+		});
+		if (rc) return rc;
 	}
-	if (rc) return rc;
-	if (e != cudaSuccess) QVZ_FAIL(h, QVZ_ERR_CUDA, "quantize egress: %s", cudaGetErrorString(e));
+	qvz_well_debug(h, "end of quantize");
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_D], h->stream));
 	int missing = 0, malformed = 0;
 	rc = take_flag(h, 2, &missing);

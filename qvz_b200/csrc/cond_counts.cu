@@ -10,16 +10,17 @@
 // clusters; its 72x72 slices live in shared memory; lanes <-> slots so global reads are coalesced; one
 // shared-memory atomic per symbol; non-zero counters are flushed with one global atomic each.
 //
-// The cost of a shared atomic is its number of conflicting lanes, and neighbouring reads agree on
-// (prev, cur) very often.  So lane L handles the 4 bytes of its word in the rotated order
-// (L&3), (L&3)+1, ... : at every step the 32 lanes are spread over the 4 column slices of the CTA and only
-// 8 of them can collide.  WIDE = 32-bit counters (K <= 2: no two bins share a word); otherwise packed
-// 16-bit pairs (5 clusters per pass; a chunk is < 65 536 slots so no counter can overflow).
+// Shared atomics: `red.shared.add 1` compiles to ATOMS.POPC.INC, which merges the lanes of a warp that hit the
+// same address (measured on B200: 1 cycle per warp instruction when the distinct addresses fall in distinct
+// banks, ~3.6 for random addresses; tools/ubench/atoms.cu).  Neighbouring reads agree on (prev, cur) very
+// often, so all lanes count the same column at the same step (few distinct addresses per instruction).
+// WIDE = 32-bit counters (K <= 2: no two bins share a word, so merging works on whole bins); otherwise
+// packed 16-bit pairs (5 clusters per pass; a chunk is < 65 536 slots so no counter can overflow).
 #include "qvz_internal.cuh"
 
 #define CC_THREADS 1024
 #define CC_BINS (72u * 72u)
-#define CC_PAD 8u                               // words between slices: the same bin of the 4 slices falls in 4 different banks
+#define CC_PAD 8u                               // words between slices
 
 __device__ __forceinline__ uint4 cc_ldg128(const uint32_t *p) {
 	uint4 v;
@@ -36,8 +37,7 @@ __device__ __forceinline__ void cc_red_shared(uint32_t addr, uint32_t v) {
 template <bool WIDE, bool TAIL>
 __device__ __forceinline__ void cc_count_chunk(const uint32_t *__restrict__ xc, const uint32_t *__restrict__ xp,
                                                const uint8_t *__restrict__ clp, uint32_t n, bool first, bool single,
-                                               uint32_t kbase, uint32_t G, const uint32_t (&sb)[4], const bool (&live)[4],
-                                               uint32_t rot8)
+                                               uint32_t kbase, uint32_t G, uint32_t tab_addr, uint32_t live)
 {
 	constexpr uint32_t SLICE = (WIDE ? CC_BINS : CC_BINS / 2) + CC_PAD;
 	for (uint32_t i = 4 * threadIdx.x; i < n; i += 4 * CC_THREADS) {
@@ -51,7 +51,7 @@ __device__ __forceinline__ void cc_count_chunk(const uint32_t *__restrict__ xc, 
 			if (ws[u] != 0u && g < G) {                  // a slot without a line holds zero words (real bytes are >= 33)
 				const uint32_t w = ws[u] - 0x21212121u;  // ingest guarantees every real byte >= 33: no borrow
 				const uint32_t pv = __funnelshift_r(qs[u] - 0x21212121u, w, 24);   // bytes: prev of byte 0, 1, 2, 3
-				const uint32_t wr = __funnelshift_r(w, w, rot8), pr = __funnelshift_r(pv, pv, rot8);
+				const uint32_t wr = w, pr = pv;
 				const uint32_t gb = single ? 0u : g * (4 * SLICE * 4);
 				// bins of bytes (0, 2) and (1, 3) as 16-bit pairs: prev*72 + cur <= 5183, times 4 still fits 16 bits
 				const uint32_t be = (pr & 0x00FF00FFu) * (WIDE ? 288u : 72u) + ((wr & 0x00FF00FFu) << (WIDE ? 2 : 0));
@@ -61,10 +61,10 @@ __device__ __forceinline__ void cc_count_chunk(const uint32_t *__restrict__ xc, 
 					const uint32_t pair = (j & 1) ? bo : be;
 					const uint32_t bin = (j & 2) ? pair >> 16 : pair & 0xFFFFu;      // WIDE: byte offset of the counter
 					if (WIDE) {
-						if (!TAIL || live[j]) cc_red_shared(sb[j] + gb + bin, 1u);
+						if (!TAIL || j < live) cc_red_shared(tab_addr + j * SLICE * 4 + gb + bin, 1u);
 					} else {
-						const uint32_t a = sb[j] + gb + ((bin << 1) & ~3u);
-						if (!TAIL || live[j]) cc_red_shared(a, 1u << (16 * (bin & 1)));
+						const uint32_t a = tab_addr + j * SLICE * 4 + gb + ((bin << 1) & ~3u);
+						if (!TAIL || j < live) cc_red_shared(a, 1u << (16 * (bin & 1)));
 					}
 				}
 			}
@@ -88,21 +88,13 @@ qvz_cond_counts_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint
 	for (uint32_t i = threadIdx.x; i < words; i += CC_THREADS) tab[i] = 0;
 	__syncthreads();
 
-	const uint32_t rot = threadIdx.x & 3;
 	const uint32_t tab_addr = (uint32_t) __cvta_generic_to_shared(tab);
-	uint32_t sb[4];                              // shared address of the slice that byte j of the ROTATED word counts into
-	bool live[4];
-#pragma unroll
-	for (uint32_t j = 0; j < 4; ++j) {
-		const uint32_t sl = (j + rot) & 3;
-		sb[j] = tab_addr + sl * SLICE * 4;
-		live[j] = 4 * c4 + sl < L.C;
-	}
+	const uint32_t live = L.C - 4 * c4;          // columns of this word that exist (>= 4 except in the last word)
 	const uint32_t *xc = Xw + (uint64_t) c4 * L.P + p0;
 	const uint32_t *xp = xc - L.P;               // only dereferenced for c4 > 0
 	const uint32_t n = (uint32_t) (p1 - p0);
-	if (4 * c4 + 3 < L.C) cc_count_chunk<WIDE, false>(xc, xp, cl + p0, n, c4 == 0, K == 1, kbase, G, sb, live, 8 * rot);
-	else cc_count_chunk<WIDE, true>(xc, xp, cl + p0, n, c4 == 0, K == 1, kbase, G, sb, live, 8 * rot);
+	if (4 * c4 + 3 < L.C) cc_count_chunk<WIDE, false>(xc, xp, cl + p0, n, c4 == 0, K == 1, kbase, G, tab_addr, live);
+	else cc_count_chunk<WIDE, true>(xc, xp, cl + p0, n, c4 == 0, K == 1, kbase, G, tab_addr, live);
 	__syncthreads();
 
 	const uint64_t per_cluster = (uint64_t) (1 + 72 * (L.C - 1)) * 72;

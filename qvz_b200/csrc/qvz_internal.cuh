@@ -63,8 +63,10 @@ struct qvz_gpu {
 	uint32_t *means_sq;      // [K] sum of squares of each centroid
 	int64_t *sums;           // [K*C + K] column sums, then line counts
 	double *moved;           // [K] device
-	double *h_moved;         // pinned [K]
-	uint32_t *h_counts;      // pinned [K]
+	double *h_moved;         // pinned [QVZ_MAX_K]
+	uint32_t *h_counts;      // pinned [QVZ_MAX_K] int64 line counts
+	uint32_t *counts_dev;    // conditional-count table of the host-pointer entry point
+	size_t means_b_cap, means_w_cap, means_sq_cap, sums_cap, moved_cap, counts_cap;
 
 	// quantize state
 	uint32_t *W;             // [K][C][72 prev][72 data] -> qv_lo | qv_hi<<8 | state_lo<<16 | state_hi<<24
@@ -81,6 +83,13 @@ struct qvz_gpu {
 	uint32_t smax;           // largest symbol value in the resident rows
 	double *Ep;              // [P] per-slot error / C
 	qvz_well_cache *well;
+
+	// host <-> device pipeline: two staging buffers, a copy stream, one event pair per buffer
+	cudaStream_t copy_stream;
+	uint8_t *stage[2];
+	size_t stage_bytes;
+	cudaEvent_t ev_copied[2], ev_consumed[2];
+	size_t Xw_cap, cl_cap, Yw_cap, Qw_cap, Dw_cap, Ep_cap, rs_cap;
 
 	// events / timings
 	cudaEvent_t ev[8];
@@ -105,13 +114,13 @@ struct qvz_gpu {
 
 #define QVZ_LAUNCHED(h) ((h)->tm.kernel_launches += 1)
 
-// layout.cu
-int qvz_layout_ingest(qvz_gpu *h, const uint8_t *raw_dev, uint32_t row_stride);
-int qvz_layout_ids_to_lines(qvz_gpu *h, uint8_t *ids_dev /* [n_lines] */);
-int qvz_layout_ids_from_lines(qvz_gpu *h, const uint8_t *ids_dev);
-int qvz_layout_words_to_lines(qvz_gpu *h, const uint32_t *Yw, uint8_t *out_dev, uint32_t out_stride,
-                              int add_newline);
-int qvz_layout_doubles_to_lines(qvz_gpu *h, const double *Ep, double *out_dev);
+// layout.cu -- every call handles the whole runs [r0, r0+nr) = lines [r0*Lr, (r0+nr)*Lr); stage_dev row 0 = line r0*Lr
+int qvz_layout_ingest(qvz_gpu *h, uint32_t r0, uint32_t nr, const uint8_t *stage_dev, uint32_t row_stride);
+int qvz_layout_ids_to_lines(qvz_gpu *h, uint32_t r0, uint32_t nr, uint8_t *stage_dev);
+int qvz_layout_ids_from_lines(qvz_gpu *h, uint32_t r0, uint32_t nr, const uint8_t *stage_dev);
+int qvz_layout_words_to_lines(qvz_gpu *h, uint32_t r0, uint32_t nr, const uint32_t *Yw, uint8_t *stage_dev,
+                              uint32_t out_stride, int add_newline);
+int qvz_layout_doubles_to_lines(qvz_gpu *h, uint32_t r0, uint32_t nr, const double *Ep, double *stage_dev);
 
 // kmeans.cu
 int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev);
@@ -124,6 +133,7 @@ int qvz_cond_counts_launch(qvz_gpu *h, uint32_t *counts_dev);
 int qvz_well_init(qvz_gpu *h);
 void qvz_well_free(qvz_gpu *h);
 int qvz_well_run_states(qvz_gpu *h, const uint32_t seed[32]);          // fills h->run_states
+void qvz_well_debug(qvz_gpu *h, const char *where);
 int qvz_well_jump_state(qvz_gpu *h, const uint32_t seed[32], uint64_t words, uint32_t *state_dev);
 
 // quantize.cu

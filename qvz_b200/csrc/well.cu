@@ -15,6 +15,8 @@
 //   P_j   = A^(2^j)                     cached per handle (squarings)
 //   M_0   = A^(words per run),  M_b = M_{b-1}^2          cached per (words per run)
 //   state[0] = A^(first word) * seed;   state[2^b + i] = M_b * state[i]      (doubling, one launch per level)
+#include <stdlib.h>
+
 #include <vector>
 
 #include "qvz_internal.cuh"
@@ -240,6 +242,27 @@ static int ensure_levels(qvz_gpu *h, uint64_t lw, uint32_t nlevels) {
 		if (rc) return rc;
 	}
 	return QVZ_OK;
+}
+
+// debugging aid (QVZ_DEBUG_WELL=1): xor checksums of the cached level tables and of the run states
+void qvz_well_debug(qvz_gpu *h, const char *where) {
+	if (!getenv("QVZ_DEBUG_WELL")) return;
+	cudaStreamSynchronize(h->stream);
+	qvz_well_cache *w = h->well;
+	std::vector<uint32_t> buf(WELL_TAB_WORDS);
+	fprintf(stderr, "[well %s] lw=%llu tabs:", where, (unsigned long long) w->lw);
+	for (size_t b = 0; b < w->level_tabs.size(); ++b) {
+		cudaMemcpy(buf.data(), w->level_tabs[b], buf.size() * 4, cudaMemcpyDeviceToHost);
+		uint32_t x = 0;
+		for (uint32_t v : buf) x = (x * 31u) ^ v;
+		fprintf(stderr, " %08x", x);
+	}
+	std::vector<uint32_t> rs((size_t) h->L.T * 32);
+	cudaMemcpy(rs.data(), h->run_states, rs.size() * 4, cudaMemcpyDeviceToHost);
+	uint32_t lo = 0, hi = 0;
+	for (size_t i = 0; i < rs.size() / 2; ++i) lo = (lo * 31u) ^ rs[i];
+	for (size_t i = rs.size() / 2; i < rs.size(); ++i) hi = (hi * 31u) ^ rs[i];
+	fprintf(stderr, " | states lo %08x hi %08x (ptr %p, tab7 %p)\n", lo, hi, (void *) h->run_states, w->level_tabs.empty() ? nullptr : (void *) w->level_tabs.back());
 }
 
 int qvz_well_run_states(qvz_gpu *h, const uint32_t seed[32]) {
