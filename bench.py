@@ -54,19 +54,16 @@ GLIBC_RAND_SEED1 = [1804289383, 846930886, 1681692777, 1714636915, 1957747793, 4
                     596516649, 1189641421]
 
 
-def make_tables(cfg, counts=None):
-    """Quantizer tables for the quantize stage.  Product path: the host codebook designer
-    (qvz_b200/host) fed with the GPU's own conditional counts; until it is built for this tree the
-    bench falls back to structurally valid staircase tables and says so in `config.tables`."""
-    try:
-        from qvz_b200 import hostlib
-        if counts is not None and hostlib.available():
-            mode = 0 if cfg["mode"] == "ratio" else 1
-            return hostlib.design_codebooks(counts, cfg["columns"], cfg["clusters"], mode, cfg["ratio"], DIST[cfg["dist"]]), "lloyd-max (host codebook designer on GPU counts)"
-    except ImportError:
-        pass
-    from tests.helpers import synthetic_tables
-    return synthetic_tables(cfg["clusters"], cfg["columns"], seed=3, dist=cfg["dist"]), "synthetic-staircase"
+def make_tables(cfg, counts):
+    """Quantizer tables for the quantize stage = what the reference's encode() would hand to start_qv_compression:
+    the host codebook designer (qvz_b200/host, bit-exact with generate_codebooks) run on the conditional counts of
+    this very workload, with the config's -f/-r target and -d distortion."""
+    from qvz_b200 import hostlib
+    mode = hostlib.MODE_RATIO if cfg["mode"] == "ratio" else hostlib.MODE_FIXED
+    t0 = time.time()
+    cb = hostlib.design_codebooks(counts, cfg["columns"], cfg["clusters"], mode, cfg["ratio"], DIST[cfg["dist"]])
+    log(f"host codebook design took {time.time()-t0:.1f}s (outside the metric, like generate_codebooks)")
+    return cb, "lloyd-max: host codebook design (bit-exact with generate_codebooks) on this workload's GPU counts"
 
 
 class ClockSampler:
@@ -160,7 +157,7 @@ def run_native(args):
         km = h.kmeans(init, cfg.get("threshold", 4.0), want_ids=False)
         counts = h.cond_counts()
     tables, tables_kind = make_tables(cfg, counts)
-    tstruct = lib.tables_struct(tables)
+    tstruct = tables.tables                         # struct qvz_flat_tables view of the designed codebooks
     log(f"[rank {rank}] k-means iterations {km['iters']}, tables: {tables_kind}")
 
     ids_host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
@@ -286,6 +283,12 @@ def run_native(args):
 
 
 # ------------------------------------------------------------------------------------------ CPU legs
+def _oracle_tables(cb):
+    """The designed codebooks as the checker's FlatTables (same arrays, no copy)."""
+    from oracle.bindings import FlatTables
+    return FlatTables(cb.clusters, cb.columns, cb.nctx, cb.ctx_of, cb.q_off, cb.qratio, cb.qmap, cb.smap, cb.distortion)
+
+
 def _cpu_sample(cfg, lines):
     from qvz_b200.synth import synth_rows
     import torch
@@ -300,16 +303,18 @@ def cpu_baseline(cfg, args):
     c, k = cfg["columns"], cfg["clusters"]
     rows = _cpu_sample(cfg, lines)
     O = Oracle()
-    tables, _ = make_tables(cfg, None)
     init = rows[[(i * 104_729 + 930_886) % lines for i in range(k)], :c]
     seed = np.full(32, 0x55555555, np.uint32)
     t0 = time.perf_counter()
     km = O.kmeans(rows, c, init, cfg.get("threshold", 4.0))
     t1 = time.perf_counter()
-    O.cond_counts(rows, c, k, km["ids"])
+    counts = O.cond_counts(rows, c, k, km["ids"])
     t2 = time.perf_counter()
-    O.quantize(rows, c, km["ids"], tables, seed, want_qv=False, want_err=True)
+    tables, _ = make_tables(cfg, counts)          # codebook design: outside the metric on both arms
+    t2b = time.perf_counter()
+    O.quantize(rows, c, km["ids"], _oracle_tables(tables), seed, want_qv=False, want_err=True)
     t3 = time.perf_counter()
+    t3 -= t2b - t2
     return {"value": round(lines * c / (t3 - t0) / 1e9, 5), "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"first {lines} lines of the workload ({t3-t0:.1f} s: kmeans {t1-t0:.2f} counts {t2-t1:.2f} quantize {t3-t2:.2f})"}
 
@@ -352,13 +357,15 @@ def run_reference(args):
     else:
         O = Oracle()
         kind = "port"
-        tables, _ = make_tables(cfg, None)
         init = rows[picks, :c]
+        km = O.kmeans(rows, c, init, cfg.get("threshold", 4.0))
+        tables, _ = make_tables(cfg, O.cond_counts(rows, c, k, km["ids"]))
+        otab = _oracle_tables(tables)
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             km = O.kmeans(rows, c, init, cfg.get("threshold", 4.0))
             O.cond_counts(rows, c, k, km["ids"])
-            O.quantize(rows, c, km["ids"], tables, seed, want_qv=False, want_err=True)
+            O.quantize(rows, c, km["ids"], otab, seed, want_qv=False, want_err=True)
             if i >= args.warmup:
                 times.append(time.perf_counter() - t0)
     sec = float(np.mean(times))

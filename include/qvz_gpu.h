@@ -114,6 +114,12 @@ int qvz_gpu_kmeans_assign_dev(qvz_gpu *h, int64_t *sums_dev);
 int qvz_gpu_kmeans_update_dev(qvz_gpu *h, const int64_t *sums_dev, double *moved_out /* K */,
                               uint32_t *counts_out /* K or NULL */);
 int qvz_gpu_kmeans_end(qvz_gpu *h, uint8_t *cluster_ids_out, uint8_t *means_out);
+/* the same two steps with the sums crossing to HOST memory, for a single process that drives several devices
+ * and adds the (<= 6 KB of) integer sums itself: assign_host copies this shard's sums out, update_host takes the
+ * totals of all shards back in and recentres. */
+int qvz_gpu_kmeans_assign_host(qvz_gpu *h, int64_t *sums_out);
+int qvz_gpu_kmeans_update_host(qvz_gpu *h, const int64_t *sums_in, double *moved_out /* K */,
+                               uint32_t *counts_out /* K or NULL */);
 
 /* ---- stage 2: conditional counts, replaces the counting loop of calculate_statistics
  *      (src/codebook.c:193-205) + pmf_increment (src/pmf.c:211-214) ----------------------- */

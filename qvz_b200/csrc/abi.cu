@@ -351,6 +351,22 @@ extern "C" int qvz_gpu_kmeans_update_dev(qvz_gpu *h, const int64_t *sums_dev, do
 	return QVZ_OK;
 }
 
+extern "C" int qvz_gpu_kmeans_assign_host(qvz_gpu *h, int64_t *sums_out) {
+	if (!h || !sums_out || !h->km_K) return QVZ_ERR_ARG;
+	int rc = qvz_gpu_kmeans_assign_dev(h, h->sums);
+	if (rc) return rc;
+	QVZ_CUDA(h, cudaMemcpyAsync(sums_out, h->sums, ((size_t) h->km_K * h->L.C + h->km_K) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+	return QVZ_OK;
+}
+
+extern "C" int qvz_gpu_kmeans_update_host(qvz_gpu *h, const int64_t *sums_in, double *moved_out, uint32_t *counts_out) {
+	if (!h || !sums_in || !h->km_K) return QVZ_ERR_ARG;
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->sums, sums_in, ((size_t) h->km_K * h->L.C + h->km_K) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+	return qvz_gpu_kmeans_update_dev(h, h->sums, moved_out, counts_out);
+}
+
 static int ids_to_host(qvz_gpu *h, uint8_t *ids_out) {
 	return pipeline_d2h(h, ids_out, 1, 1, [&](const piece &pc) {
 		return qvz_layout_ids_to_lines(h, pc.r0, pc.nr, h->stage[pc.buf]);

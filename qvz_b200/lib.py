@@ -24,6 +24,7 @@ EXPORTS = [
     "qvz_gpu_open", "qvz_gpu_close", "qvz_gpu_last_error", "qvz_gpu_stream", "qvz_gpu_get_timings",
     "qvz_gpu_reset_launch_count", "qvz_gpu_load_rows", "qvz_gpu_kmeans", "qvz_gpu_set_clusters",
     "qvz_gpu_kmeans_begin", "qvz_gpu_kmeans_assign_dev", "qvz_gpu_kmeans_update_dev", "qvz_gpu_kmeans_end",
+    "qvz_gpu_kmeans_assign_host", "qvz_gpu_kmeans_update_host",
     "qvz_gpu_cond_counts", "qvz_gpu_cond_counts_dev", "qvz_gpu_cond_counts_len", "qvz_gpu_quantize",
     "qvz_gpu_well_jump",
 ]
@@ -101,6 +102,10 @@ def load() -> C.CDLL:
     L.qvz_gpu_kmeans_assign_dev.argtypes = [vp, vp]
     L.qvz_gpu_kmeans_update_dev.restype = C.c_int
     L.qvz_gpu_kmeans_update_dev.argtypes = [vp, vp, f64p, u32p]
+    L.qvz_gpu_kmeans_assign_host.restype = C.c_int
+    L.qvz_gpu_kmeans_assign_host.argtypes = [vp, i64p]
+    L.qvz_gpu_kmeans_update_host.restype = C.c_int
+    L.qvz_gpu_kmeans_update_host.argtypes = [vp, i64p, f64p, u32p]
     L.qvz_gpu_kmeans_end.restype = C.c_int
     L.qvz_gpu_kmeans_end.argtypes = [vp, u8p, u8p]
     L.qvz_gpu_cond_counts.restype = C.c_int
