@@ -171,6 +171,7 @@ def run_native(args):
             torch.cuda.synchronize()
 
     def step_resident():
+        h.prefetch_draws(seed)                     # the draws depend on the seed only: generated under k-means / counts
         if fe:
             fe.kmeans(init, cfg.get("threshold", 4.0), want_ids=False)
             fe.cond_counts(want_host=False)
@@ -185,6 +186,7 @@ def run_native(args):
 
     def step_e2e():
         h.load_rows(rows, n, c, c + 1, first_line=first_line)
+        h.prefetch_draws(seed)
         if fe:
             fe.kmeans(init, cfg.get("threshold", 4.0), want_ids=True)
             fe.cond_counts(want_host=True)
@@ -256,7 +258,7 @@ def run_native(args):
     dur_ms, alg_bytes = kern[dom]
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None,
+                "frac": round(achieved / peak, 4), "traffic": ncu_traffic(dom, cfg),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "per_kernel_GBps": {kk: round(b / (d * 1e-3) / 1e9, 1) for kk, (d, b) in kern.items() if d > 0},
                 "algorithmic_bytes_per_launch": alg_bytes}
@@ -280,6 +282,22 @@ def run_native(args):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel, cfg):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of this very workload (profiles/*_ncu_full_cfg2.json); None when the workload is not the captured one."""
+    import glob
+    if (cfg["name"], cfg["lines"], cfg["columns"], cfg["clusters"]) != ("cfg2", 20_000_000, 150, 1):
+        return None
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full_cfg2.json")))
+    if not files:
+        return None
+    per = json.load(open(files[-1]))["dram_bytes_per_launch"]
+    pick = {"quantize": ("qvz_draws_kernel", "qvz_quantize_batched_kernel"), "cond_counts": ("qvz_cond_counts_kernel",),
+            "kmeans_assign": ("qvz_kmeans_single_kernel", "qvz_kmeans_assign_kernel")}[kernel]
+    tot = sum(v for k, v in per.items() if any(p in k for p in pick))
+    return int(tot) if tot else None
 
 
 # ------------------------------------------------------------------------------------------ CPU legs

@@ -70,9 +70,9 @@ struct qvz_gpu_timings {
 	float kmeans_ms;             /* all iterations: assign+accumulate and recenter kernels       */
 	float kmeans_assign_ms;      /* sum over iterations of the assign+accumulate kernel alone    */
 	float cond_counts_ms;        /* conditional-count kernel(s) incl. table zeroing              */
-	float quantize_setup_ms;     /* table upload + WELL jump-ahead                               */
-	float quantize_ms;           /* quantize walk: draw generation + walk kernels                */
-	float quantize_draws_ms;     /* of which: WELL draw generation kernel (0 on the line-major path) */
+	float quantize_setup_ms;     /* main stream before the walk: table upload/composition, waiting for the draws */
+	float quantize_ms;           /* quantize_draws_ms + duration of the walk kernel              */
+	float quantize_draws_ms;     /* WELL jump-ahead + draw generation (auxiliary stream, overlapped) */
 	float quantize_d2h_ms;       /* output re-layout + device->host copies                       */
 	uint32_t kmeans_iters;
 	uint32_t kernel_launches;    /* kernels launched by this handle since the last reset         */
@@ -141,6 +141,12 @@ uint64_t qvz_gpu_cond_counts_len(uint32_t K, uint32_t columns);   /* number of u
  *   caller adds them in line order and divides by the line count to get *dis. */
 int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, const uint32_t well_seed[32],
                      uint8_t *symbols_out, uint8_t *qv_out, double *line_err_out);
+
+/* Optional: start generating the WELL draws for `well_seed` now, on the handle's auxiliary stream.  The draws
+ * depend only on the seed and on the resident rows' shape, so a caller that knows the seed early (the reference
+ * draws it right before start_qv_compression, src/qv_stream.c:76-90, but nothing depends on that order) can overlap
+ * their generation with k-means / counting / codebook design.  qvz_gpu_quantize with the same seed then uses them. */
+int qvz_gpu_prefetch_draws(qvz_gpu *h, const uint32_t well_seed[32]);
 
 /* ---- WELL1024a helpers (src/well.c:8-24), used by tests and by the decoder-side host ------ */
 /* state_out = state after `words` calls of well_1024a starting from seed (n = 0 frame). */

@@ -192,6 +192,10 @@ extern "C" int qvz_gpu_open(qvz_gpu **out, int device) {
 	QVZ_CUDA(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
 	QVZ_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 	QVZ_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+	QVZ_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+	QVZ_CUDA(h, cudaEventCreate(&h->ev_draws_start));
+	QVZ_CUDA(h, cudaEventCreate(&h->ev_draws));
+	QVZ_CUDA(h, cudaEventCreateWithFlags(&h->ev_walk_done, cudaEventDisableTiming));
 	for (int i = 0; i < 8; ++i) QVZ_CUDA(h, cudaEventCreate(&h->ev[i]));
 	for (int b = 0; b < 2; ++b) {
 		QVZ_CUDA(h, cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
@@ -209,7 +213,12 @@ extern "C" void qvz_gpu_close(qvz_gpu *h) {
 	cudaSetDevice(h->device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+	if (h->aux_stream) cudaStreamSynchronize(h->aux_stream);
 	release_rows(h);
+	if (h->ev_draws_start) cudaEventDestroy(h->ev_draws_start);
+	if (h->ev_draws) cudaEventDestroy(h->ev_draws);
+	if (h->ev_walk_done) cudaEventDestroy(h->ev_walk_done);
+	if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
 	for (int b = 0; b < 2; ++b) {
 		free_dev(h->stage[b]);
 		if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
@@ -260,6 +269,8 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 	if (first_line & 3) QVZ_FAIL(h, QVZ_ERR_ARG, "load_rows: first_line must be a multiple of 4");
 	QVZ_CUDA(h, cudaSetDevice(h->device));
 	h->K = 0;                                    // the resident cluster ids belong to the previous rows
+	QVZ_CUDA(h, cudaStreamSynchronize(h->aux_stream));
+	h->draws_state = 0;                          // ... and so do prefetched draws
 
 	qvz_layout &L = h->L;
 	L.n_lines = n_lines;
@@ -525,6 +536,44 @@ static int upload_tables(qvz_gpu *h, const struct qvz_flat_tables *t, int *toepl
 	                            h->flat + o_smap);
 }
 
+// WELL jump-ahead + draw generation depend on the seed and the layout only -- not on the rows, the clusters or the
+// tables -- so they run on their own stream, overlapped with whatever the main stream is doing (table upload and
+// composition inside qvz_gpu_quantize; k-means / counts when the caller prefetches).  draws_state: 0 = nothing,
+// 1 = run states only, 2 = run states + draws, for draws_seed.
+static int start_draws(qvz_gpu *h, const uint32_t seed[32], bool with_draws) {
+	const qvz_layout &L = h->L;
+	int rc = ensure_buf(h, &h->run_states, &h->rs_cap, (size_t) L.T * 32 * sizeof(uint32_t));
+	if (!rc && with_draws) rc = ensure_buf(h, &h->Dw, &h->Dw_cap, (size_t) L.C4 * L.P * sizeof(uint32_t));
+	if (rc) return rc;
+	if (h->walk_recorded) QVZ_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->ev_walk_done, 0));   // the last walk still reads Dw
+	cudaStream_t main_stream = h->stream;
+	h->stream = h->aux_stream;                   // well.cu / quantize.cu launch on h->stream
+	cudaError_t e = cudaEventRecord(h->ev_draws_start, h->aux_stream);
+	if (e == cudaSuccess) rc = qvz_well_run_states(h, seed);
+	if (e == cudaSuccess && !rc && with_draws) rc = qvz_quantize_draws(h);
+	if (e == cudaSuccess && !rc) e = cudaEventRecord(h->ev_draws, h->aux_stream);
+	h->stream = main_stream;
+	if (rc) return rc;
+	if (e != cudaSuccess) QVZ_FAIL(h, QVZ_ERR_CUDA, "draw generation: %s", cudaGetErrorString(e));
+	memcpy(h->draws_seed, seed, sizeof(h->draws_seed));
+	h->draws_state = with_draws ? 2 : 1;
+	return QVZ_OK;
+}
+
+// the batched walk is possible for some A >= the lower bound smax + 2 (see qvz_gpu_quantize)
+static bool batched_possible(const qvz_gpu *h, uint32_t clusters) {
+	uint32_t A = (h->smax + 2) & ~1u;
+	if (A > 72) A = 72;
+	return !getenv("QVZ_FORCE_LINE_MAJOR") && qvz_quantize_batched_group(clusters, A) > 0;
+}
+
+extern "C" int qvz_gpu_prefetch_draws(qvz_gpu *h, const uint32_t well_seed[32]) {
+	if (!h || !well_seed) return QVZ_ERR_ARG;
+	if (!h->Xw) QVZ_FAIL(h, QVZ_ERR_ARG, "prefetch_draws: no rows loaded");
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	return start_draws(h, well_seed, batched_possible(h, h->K ? h->K : 1));
+}
+
 extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, const uint32_t well_seed[32],
                                 uint8_t *symbols_out, uint8_t *qv_out, double *line_err_out)
 {
@@ -538,16 +587,18 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	int rc = ensure_buf(h, &h->Yw, &h->Yw_cap, wbytes);
 	if (!rc && qv_out) rc = ensure_buf(h, &h->Qw, &h->Qw_cap, wbytes);
 	if (!rc) rc = ensure_buf(h, &h->Ep, &h->Ep_cap, (size_t) L.P * sizeof(double));   // the walk always sums the distortion, like the reference
-	if (!rc) rc = ensure_buf(h, &h->run_states, &h->rs_cap, (size_t) L.T * 32 * sizeof(uint32_t));
 	if (rc) return rc;
 
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
+	// draws first (aux stream), unless a prefetch for this seed is already in flight or done
+	const bool prefetched = h->draws_state && memcmp(h->draws_seed, well_seed, sizeof(h->draws_seed)) == 0;
+	if (!prefetched) {
+		rc = start_draws(h, well_seed, batched_possible(h, t->clusters));
+		if (rc) return rc;
+	}
 	int toeplitz = 0;
 	rc = upload_tables(h, t, &toeplitz);
 	if (rc) return rc;
-	rc = qvz_well_run_states(h, well_seed);
-	if (rc) return rc;
-	qvz_well_debug(h, "after run_states");
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
 	// Fast path: compact the tables to the A x A box of values that can occur and walk column-synchronously
 	// from shared memory (quantize.cu).  A-1 = max(largest symbol in the rows, largest reachable quantized value).
@@ -572,24 +623,24 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 				QVZ_CUDA(h, cudaMalloc(&h->G, gbytes));
 				h->G_cap = gbytes;
 			}
-			rc = ensure_buf(h, &h->Dw, &h->Dw_cap, wbytes);
-			if (rc) return rc;
 			rc = qvz_quantize_compact(h, t->clusters, t->columns, A);
 			if (rc) return rc;
+			if (h->draws_state != 2) {               // the lower bound on A said "line-major" but the tables allow the batched walk
+				rc = start_draws(h, well_seed, true);
+				if (rc) return rc;
+			}
 		}
 	}
-	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_E], h->stream));
-	if (batched) {
-		rc = qvz_quantize_draws(h);
-		if (rc) return rc;
-		QVZ_CUDA(h, cudaEventRecord(h->ev[EV_F], h->stream));
-		rc = qvz_quantize_launch_batched(h, t->clusters, A, qv_out != nullptr, toeplitz);
-	} else {
-		QVZ_CUDA(h, cudaEventRecord(h->ev[EV_F], h->stream));
-		rc = qvz_quantize_launch(h, qv_out != nullptr, 1, toeplitz);
-	}
+	QVZ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_draws, 0));      // run states (+ draws) are ready
+	qvz_well_debug(h, "after run_states");
+	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_F], h->stream));
+	if (batched) rc = qvz_quantize_launch_batched(h, t->clusters, A, qv_out != nullptr, toeplitz);
+	else rc = qvz_quantize_launch(h, qv_out != nullptr, 1, toeplitz);
 	if (rc) return rc;
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));
+	QVZ_CUDA(h, cudaEventRecord(h->ev_walk_done, h->stream));
+	h->walk_recorded = 1;
+	h->draws_state = 0;                          // one generation serves one walk (a new call may bring a new seed)
 
 	// egress: packed -> line-major pieces on the device, each copied to the host while the next is re-laid out
 	if (symbols_out) {
@@ -618,9 +669,13 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	rc = take_flag(h, 3, &malformed);
 	if (rc) return rc;
 	if (malformed) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: malformed flat tables (context index or quantized value out of range)");
-	h->tm.quantize_setup_ms = ev_ms(h, EV_A, EV_E);
-	h->tm.quantize_ms = ev_ms(h, EV_E, EV_C);
-	h->tm.quantize_draws_ms = ev_ms(h, EV_E, EV_F);
+	// setup = everything on the main stream before the walk (table upload/composition, waiting for the draws);
+	// draws = jump-ahead + draw generator on the aux stream (overlapped); quantize = draws + walk kernel durations
+	float draws_ms = 0.f;
+	cudaEventElapsedTime(&draws_ms, h->ev_draws_start, h->ev_draws);
+	h->tm.quantize_setup_ms = ev_ms(h, EV_A, EV_F);
+	h->tm.quantize_draws_ms = draws_ms;
+	h->tm.quantize_ms = draws_ms + ev_ms(h, EV_F, EV_C);
 	h->tm.quantize_d2h_ms = ev_ms(h, EV_C, EV_D);
 	if (missing) QVZ_FAIL(h, QVZ_ERR_CONTEXT, "quantize: reached a context without a quantizer (the reference asserts, src/codebook.c:164)");
 	return QVZ_OK;

@@ -84,6 +84,12 @@ struct qvz_gpu {
 	double *Ep;              // [P] per-slot error / C
 	qvz_well_cache *well;
 
+	// draw generation overlapped on its own stream (abi.cu:start_draws)
+	cudaStream_t aux_stream;
+	cudaEvent_t ev_draws_start, ev_draws, ev_walk_done;
+	int draws_state, walk_recorded;
+	uint32_t draws_seed[32];
+
 	// host <-> device pipeline: two staging buffers, a copy stream, one event pair per buffer
 	cudaStream_t copy_stream;
 	uint8_t *stage[2];

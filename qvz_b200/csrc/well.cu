@@ -70,8 +70,8 @@ qvz_f2_apply_kernel(const uint32_t *__restrict__ tab, const uint32_t *__restrict
 	if (v >= count) return;
 	const uint32_t mine = in[(uint64_t) v * 32 + lane];
 	uint32_t acc = 0;
-#pragma unroll 8
-	for (uint32_t pos = 0; pos < 128; ++pos) {
+#pragma unroll 32
+	for (uint32_t pos = 0; pos < 128; ++pos) {          // the 128 row loads are independent: keep 32 in flight
 		const uint32_t w = __shfl_sync(0xFFFFFFFFu, mine, pos >> 2);
 		const uint32_t b = (w >> (8 * (pos & 3))) & 0xFFu;
 		acc ^= __ldg(&tab[(pos * 256 + b) * 32 + lane]);

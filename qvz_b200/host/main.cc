@@ -136,6 +136,17 @@ static void encode(const char *input_name, const char *output_name, options *opt
 		memcpy(&means[(size_t) j * C], file + (block_id * MAX_LINES_PER_BLOCK + line_id) * (C + 1), C);
 		if (opts->verbose) printf("Chose block %d, line %d.\n", block_id, line_id);
 	}
+	// initialize_arithStream (src/qv_stream.c:76-90): the WELL seed is 32 rand() values after srand(time(0)), drawn
+	// AFTER the k-means picks above consumed the unseeded rand() stream; -DDEBUG builds of the reference use
+	// 0x55555555 instead, selected here with QVZ_DEBUG_SEED=1.  Nothing else depends on the seed, so it is drawn
+	// now and the devices generate their draws underneath k-means, counting and codebook design.
+	uint32_t seed[32];
+	srand((uint32_t) time(0));
+	for (int i = 0; i < 32; ++i) seed[i] = getenv("QVZ_DEBUG_SEED") ? 0x55555555u : (uint32_t) rand();
+	for (auto &s : sh) {
+		int rc = qvz_gpu_prefetch_draws(s.h, seed);
+		if (rc) die_gpu(s.h, "qvz_gpu_prefetch_draws", rc);
+	}
 	std::vector<uint8_t> ids(lines);
 	uint32_t iter_count = 0;
 	if (ngpu == 1) {
@@ -214,11 +225,6 @@ static void encode(const char *input_name, const char *output_name, options *opt
 	if (opts->verbose) printf("Stats and codebook generation took %.4f seconds\n", now() - t_stats);
 
 	// ---- write_codebooks + start_qv_compression
-	// initialize_arithStream (src/qv_stream.c:76-90): the WELL seed is 32 rand() values after srand(time(0));
-	// -DDEBUG builds of the reference use 0x55555555 instead, selected here with QVZ_DEBUG_SEED=1
-	uint32_t seed[32];
-	srand((uint32_t) time(0));
-	for (int i = 0; i < 32; ++i) seed[i] = getenv("QVZ_DEBUG_SEED") ? 0x55555555u : (uint32_t) rand();
 	struct qvz_flat_tables tables;
 	qvz_host_tables(cb, &tables);
 	std::vector<uint8_t> symbols((size_t) lines * C), qv;

@@ -26,6 +26,7 @@ EXPORTS = [
     "qvz_gpu_kmeans_begin", "qvz_gpu_kmeans_assign_dev", "qvz_gpu_kmeans_update_dev", "qvz_gpu_kmeans_end",
     "qvz_gpu_kmeans_assign_host", "qvz_gpu_kmeans_update_host",
     "qvz_gpu_cond_counts", "qvz_gpu_cond_counts_dev", "qvz_gpu_cond_counts_len", "qvz_gpu_quantize",
+    "qvz_gpu_prefetch_draws",
     "qvz_gpu_well_jump",
 ]
 
@@ -116,6 +117,8 @@ def load() -> C.CDLL:
     L.qvz_gpu_cond_counts_len.argtypes = [C.c_uint32, C.c_uint32]
     L.qvz_gpu_quantize.restype = C.c_int
     L.qvz_gpu_quantize.argtypes = [vp, C.POINTER(FlatTablesStruct), u32p, vp, vp, vp]
+    L.qvz_gpu_prefetch_draws.restype = C.c_int
+    L.qvz_gpu_prefetch_draws.argtypes = [vp, u32p]
     L.qvz_gpu_well_jump.restype = C.c_int
     L.qvz_gpu_well_jump.argtypes = [vp, u32p, C.c_uint64, u32p]
     _lib = L
@@ -232,6 +235,10 @@ class Handle:
         st = tables if isinstance(tables, FlatTablesStruct) else tables_struct(tables)
         self._check(self.L.qvz_gpu_quantize(self.h, C.byref(st), _p(seed, u32p), _addr(sym), _addr(qv), _addr(err)))
         return dict(symbols=sym, qv=qv, line_err=err)
+
+    def prefetch_draws(self, seed):
+        seed = np.ascontiguousarray(seed, dtype=np.uint32)
+        self._check(self.L.qvz_gpu_prefetch_draws(self.h, _p(seed, u32p)))
 
     def well_jump(self, seed, words: int) -> np.ndarray:
         seed = np.ascontiguousarray(seed, dtype=np.uint32)
