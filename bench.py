@@ -171,7 +171,6 @@ def run_native(args):
             torch.cuda.synchronize()
 
     def step_resident():
-        h.prefetch_draws(seed)                     # the draws depend on the seed only: generated under k-means / counts
         if fe:
             fe.kmeans(init, cfg.get("threshold", 4.0), want_ids=False)
             fe.cond_counts(want_host=False)
@@ -186,7 +185,6 @@ def run_native(args):
 
     def step_e2e():
         h.load_rows(rows, n, c, c + 1, first_line=first_line)
-        h.prefetch_draws(seed)
         if fe:
             fe.kmeans(init, cfg.get("threshold", 4.0), want_ids=True)
             fe.cond_counts(want_host=True)

@@ -72,7 +72,7 @@ struct qvz_gpu_timings {
 	float cond_counts_ms;        /* conditional-count kernel(s) incl. table zeroing              */
 	float quantize_setup_ms;     /* main stream before the walk: table upload/composition, waiting for the draws */
 	float quantize_ms;           /* quantize_draws_ms + duration of the walk kernel              */
-	float quantize_draws_ms;     /* WELL jump-ahead + draw generation (auxiliary stream, overlapped) */
+	float quantize_draws_ms;     /* WELL draw generator kernel (auxiliary stream, overlapped with the setup) */
 	float quantize_d2h_ms;       /* output re-layout + device->host copies                       */
 	uint32_t kmeans_iters;
 	uint32_t kernel_launches;    /* kernels launched by this handle since the last reset         */

@@ -195,6 +195,7 @@ extern "C" int qvz_gpu_open(qvz_gpu **out, int device) {
 	QVZ_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
 	QVZ_CUDA(h, cudaEventCreate(&h->ev_draws_start));
 	QVZ_CUDA(h, cudaEventCreate(&h->ev_draws));
+	QVZ_CUDA(h, cudaEventCreate(&h->ev_jump_done));
 	QVZ_CUDA(h, cudaEventCreateWithFlags(&h->ev_walk_done, cudaEventDisableTiming));
 	for (int i = 0; i < 8; ++i) QVZ_CUDA(h, cudaEventCreate(&h->ev[i]));
 	for (int b = 0; b < 2; ++b) {
@@ -217,6 +218,7 @@ extern "C" void qvz_gpu_close(qvz_gpu *h) {
 	release_rows(h);
 	if (h->ev_draws_start) cudaEventDestroy(h->ev_draws_start);
 	if (h->ev_draws) cudaEventDestroy(h->ev_draws);
+	if (h->ev_jump_done) cudaEventDestroy(h->ev_jump_done);
 	if (h->ev_walk_done) cudaEventDestroy(h->ev_walk_done);
 	if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
 	for (int b = 0; b < 2; ++b) {
@@ -550,6 +552,7 @@ static int start_draws(qvz_gpu *h, const uint32_t seed[32], bool with_draws) {
 	h->stream = h->aux_stream;                   // well.cu / quantize.cu launch on h->stream
 	cudaError_t e = cudaEventRecord(h->ev_draws_start, h->aux_stream);
 	if (e == cudaSuccess) rc = qvz_well_run_states(h, seed);
+	if (e == cudaSuccess && !rc) e = cudaEventRecord(h->ev_jump_done, h->aux_stream);
 	if (e == cudaSuccess && !rc && with_draws) rc = qvz_quantize_draws(h);
 	if (e == cudaSuccess && !rc) e = cudaEventRecord(h->ev_draws, h->aux_stream);
 	h->stream = main_stream;
@@ -670,9 +673,9 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	if (rc) return rc;
 	if (malformed) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: malformed flat tables (context index or quantized value out of range)");
 	// setup = everything on the main stream before the walk (table upload/composition, waiting for the draws);
-	// draws = jump-ahead + draw generator on the aux stream (overlapped); quantize = draws + walk kernel durations
+	// draws = draw generator kernel on the aux stream (overlapped with the setup); quantize = draws + walk kernel durations
 	float draws_ms = 0.f;
-	cudaEventElapsedTime(&draws_ms, h->ev_draws_start, h->ev_draws);
+	cudaEventElapsedTime(&draws_ms, h->ev_jump_done, h->ev_draws);      // the draw generator kernel alone (jump-ahead is setup)
 	h->tm.quantize_setup_ms = ev_ms(h, EV_A, EV_F);
 	h->tm.quantize_draws_ms = draws_ms;
 	h->tm.quantize_ms = draws_ms + ev_ms(h, EV_F, EV_C);

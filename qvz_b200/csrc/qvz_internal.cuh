@@ -86,7 +86,7 @@ struct qvz_gpu {
 
 	// draw generation overlapped on its own stream (abi.cu:start_draws)
 	cudaStream_t aux_stream;
-	cudaEvent_t ev_draws_start, ev_draws, ev_walk_done;
+	cudaEvent_t ev_draws_start, ev_jump_done, ev_draws, ev_walk_done;
 	int draws_state, walk_recorded;
 	uint32_t draws_seed[32];
 
