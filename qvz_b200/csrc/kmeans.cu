@@ -14,79 +14,126 @@
 //              CTA-level uint32 partials in shared memory, one 64-bit global atomic per (cluster, column,
 //              CTA).  Integer sums are order independent.
 //   recenter:  mean = (uint8)(sum / count), moved_k = sum (new-old)^2 -- tiny second kernel.
+#include <stdlib.h>
+
 #include "qvz_internal.cuh"
 
 // Shared-memory plan of one CTA (R = blockDim.x rows per tile):
-//   mean_s[K][C4]  msq[K]  cnt[K]  acc[K][C4*4]  off[(NW+1)*K + 1]  perm[R] (u16)  tile[C4][R+1]
+//   bar  tile[C4][R+4]  stile[C4][R+1]  mean4[C4][KP]  acc[K][C4*4]  msq[KP]  cnt[K]  off[(NW+2)*K]
 // Per tile of R slots:
-//   phase 1  thread <-> row: load the row's packed words (coalesced across the warp), park them in
-//            tile[c4][row] (pitch R+1: conflict free both ways), K dp4a per word, argmin;
-//   sort     counting sort of the tile's rows by cluster (ballot/popc ranks + a tiny scan) -> perm[];
-//   phase 2  thread <-> (column word, part): walks the cluster-contiguous row lists, adding the packed
-//            16-bit halves (<= 256 rows x 255 < 2^16), one 4-way unpack + shared atomic per (cluster, word).
+//   load     the C4 rows of the tile (R*4 contiguous bytes of each word column) arrive by TMA bulk copies
+//            (cp.async.bulk + mbarrier); the copy of tile n+1 is issued as soon as tile n has been scattered, so
+//            it flies under phase 2 and HBM never idles on a barrier;
+//   phase 1  thread <-> row: its packed words come from shared memory (lane-consecutive: conflict free), the K
+//            centroid words of a column are one or two 16-byte broadcast loads, K dp4a per word, argmin;
+//   sort     counting sort of the tile's rows by cluster (ballot/popc ranks + a tiny scan) gives every row its
+//            sorted position; the row's words are scattered there (stile: rows of one cluster are contiguous);
+//   phase 2  thread <-> (column word, part): walks the contiguous row range of each cluster, one dp4a per
+//            (word, column) against a one-hot byte selector (exact 32-bit sums, no unpacking), then one shared
+//            atomic per (cluster, column).  Pitch R+1 makes the 32 column words of a warp fall in 32 banks.
+//            (A warp-REDUX formulation over sorted rows was measured 2x slower: REDUX.SUM is a slow path.)
+__device__ __forceinline__ uint32_t km_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
 template <int KT>
 __global__ void __launch_bounds__(QVZ_THREADS)
 qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t *__restrict__ cl,
                          const uint32_t *__restrict__ means_w, const uint32_t *__restrict__ means_sq,
                          uint32_t Krt, unsigned long long *__restrict__ sums)
 {
+	constexpr int KMAX = KT > 0 ? KT : QVZ_MAX_K;
+	constexpr uint32_t KP = (KMAX + 3) & ~3;             // clusters padded to whole uint4s
 	const uint32_t K = KT > 0 ? (uint32_t) KT : Krt;
-	const uint32_t C4 = L.C4, R = blockDim.x, NW = R >> 5, pitch = R + 1;
-	extern __shared__ uint32_t sm[];
-	uint32_t *mean_s = sm;                       // [K][C4]
-	uint32_t *msq = mean_s + K * C4;             // [K]
-	uint32_t *cnt = msq + K;                     // [K]
-	uint32_t *acc = cnt + K;                     // [K][C4*4]
-	uint32_t *off = acc + K * C4 * 4;            // [(NW+1)][K] exclusive offsets, then [K] totals scratch
-	uint16_t *perm = (uint16_t *) (off + (NW + 1) * K + 1);
-	uint32_t *tile = (uint32_t *) (perm + R + (R & 1));
+	const uint32_t C4 = L.C4, R = blockDim.x, NW = R >> 5;
+	const uint32_t pitch = R + 4, spitch = R + 1;
+	extern __shared__ __align__(16) uint32_t sm[];
+	uint64_t *bar = (uint64_t *) sm;
+	uint32_t *tile = sm + 4;                             // [C4][pitch]   (TMA destination: 16-byte aligned rows)
+	uint32_t *stile = tile + C4 * pitch;                 // [C4][spitch]  rows sorted by cluster
+	uint32_t *mean4 = stile + ((C4 * spitch + 3) & ~3u); // [C4][KP]
+	uint32_t *acc = mean4 + C4 * KP;                     // [K][C4*4]
+	uint32_t *msq = acc + K * C4 * 4;                    // [KP]
+	uint32_t *cnt = msq + KP;                            // [K]
+	uint32_t *off = cnt + K;                             // [(NW+1)][K] exclusive offsets, then [K] totals
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	for (uint32_t i = tid; i < K * C4; i += R) mean_s[i] = means_w[i];
+	for (uint32_t i = tid; i < C4 * KP; i += R) {
+		const uint32_t c4 = i / KP, k = i - c4 * KP;
+		mean4[i] = k < K ? means_w[k * C4 + c4] : 0u;
+	}
 	for (uint32_t i = tid; i < K * C4 * 4; i += R) acc[i] = 0;
-	if (tid < K) {
-		cnt[tid] = 0;
-		msq[tid] = means_sq[tid];
+	if (tid < KP) msq[tid] = tid < K ? means_sq[tid] : 0u;
+	if (tid < K) cnt[tid] = 0;
+	if (tid == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(km_smem_u32(bar)));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
 	const uint32_t nparts = (R / C4) ? (R / C4) : 1;
-	for (uint64_t base = (uint64_t) blockIdx.x * R; base < L.P; base += (uint64_t) gridDim.x * R) {
-		const uint64_t p = base + tid;               // P is a multiple of 256 and of R
+	const uint64_t tiles = L.P / R;                      // P % 4096 == 0 and R | 256
+	const uint32_t tile_bytes = C4 * R * 4;
+	auto fetch = [&](uint64_t t) {                       // word column c4 of tile t: R*4 contiguous bytes
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the tile's earlier generic reads are done (barrier before)
+		if (tid == 0)
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(km_smem_u32(bar)), "r"(tile_bytes) : "memory");
+		for (uint32_t c4 = tid; c4 < C4; c4 += R)
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			             ::"r"(km_smem_u32(tile + c4 * pitch)), "l"(Xw + (uint64_t) c4 * L.P + t * R), "r"(R * 4),
+			               "r"(km_smem_u32(bar)) : "memory");
+	};
+	if (blockIdx.x < tiles) fetch(blockIdx.x);
+
+	uint32_t it = 0;
+	for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+		{                                                // wait for this tile's bytes
+			const uint32_t parity = it & 1, addr = km_smem_u32(bar);
+			asm volatile(
+			    "{\n"
+			    ".reg .pred p;\n"
+			    "KW_%=:\n"
+			    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+			    "@p bra KD_%=;\n"
+			    "bra KW_%=;\n"
+			    "KD_%=:\n"
+			    "}" ::"r"(addr), "r"(parity) : "memory");
+		}
+		const uint64_t p = t * R + tid;
 		const bool valid = cl[p] != QVZ_NO_LINE;
 		uint32_t best = 0;
 		{
-			uint32_t D[KT > 0 ? KT : QVZ_MAX_K];
+			uint32_t D[KP];
 #pragma unroll
-			for (int k = 0; k < (KT > 0 ? KT : QVZ_MAX_K); ++k) D[k] = 0;
-			const uint32_t *xp = Xw + p;
-			uint32_t *tp = tile + tid;
+			for (uint32_t k = 0; k < KP; ++k) D[k] = 0;
+			const uint32_t *tp = tile + tid;
 #pragma unroll 4
 			for (uint32_t c4 = 0; c4 < C4; ++c4) {
-				const uint32_t w = xp[(uint64_t) c4 * L.P];
-				tp[c4 * pitch] = w;
-				if (KT != 1) {
+				const uint32_t w = tp[c4 * pitch];
+				const uint4 *m = (const uint4 *) (mean4 + c4 * KP);
 #pragma unroll
-					for (int k = 0; k < (KT > 0 ? KT : QVZ_MAX_K); ++k)
-						if (KT > 0 || (uint32_t) k < K) D[k] = __dp4a(w, mean_s[k * C4 + c4], D[k]);
+				for (uint32_t g = 0; g < KP / 4; ++g) {
+					if (KT > 0 || 4 * g < K) {
+						const uint4 mm = m[g];
+						D[4 * g + 0] = __dp4a(w, mm.x, D[4 * g + 0]);
+						D[4 * g + 1] = __dp4a(w, mm.y, D[4 * g + 1]);
+						D[4 * g + 2] = __dp4a(w, mm.z, D[4 * g + 2]);
+						D[4 * g + 3] = __dp4a(w, mm.w, D[4 * g + 3]);
+					}
 				}
 			}
-			if (KT != 1) {
-				int bestv = (int) msq[0] - 2 * (int) D[0];
+			int bestv = (int) msq[0] - 2 * (int) D[0];
 #pragma unroll
-				for (int k = 1; k < (KT > 0 ? KT : QVZ_MAX_K); ++k) {
-					if (KT > 0 || (uint32_t) k < K) {
-						const int v = (int) msq[k] - 2 * (int) D[k];
-						if (v < bestv) {             // strict '<': lowest cluster id wins ties (assign_cluster)
-							bestv = v;
-							best = k;
-						}
+			for (uint32_t k = 1; k < (uint32_t) KMAX; ++k) {
+				if (KT > 0 || k < K) {
+					const int v = (int) msq[k] - 2 * (int) D[k];
+					if (v < bestv) {                 // strict '<': lowest cluster id wins ties (assign_cluster)
+						bestv = v;
+						best = k;
 					}
 				}
 			}
 		}
 		if (valid) cl[p] = (uint8_t) best;
-		const uint32_t key = valid ? best : 0;       // empty slots hold zero words: harmless in any list
+		const uint32_t key = valid ? best : 0;           // empty slots hold zero words: harmless in any list
 
 		// counting sort by cluster
 		uint32_t rank = 0;
@@ -98,7 +145,7 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
 			if (lane == 0 && nv) atomicAdd(&cnt[k], nv);
 		}
 		__syncthreads();
-		if (tid < K) {                               // column k: running sum over warps, totals in the last row
+		if (tid < K) {                                   // column k: running sum over warps, totals in the last row
 			uint32_t run = 0;
 			for (uint32_t w = 0; w < NW; ++w) {
 				const uint32_t c = off[(w + 1) * K + tid];
@@ -108,37 +155,48 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
 			off[NW * K + tid] = run;
 		}
 		__syncthreads();
-		{
-			uint32_t start = 0;
-			for (uint32_t k = 0; k < key; ++k) start += off[NW * K + k];
-			perm[start + off[warp * K + key] + rank] = (uint16_t) tid;
+		{                                                // scatter this row to its sorted position
+			uint32_t spos = off[warp * K + key] + rank;
+			for (uint32_t k = 0; k < key; ++k) spos += off[NW * K + k];
+			const uint32_t *tp = tile + tid;
+			uint32_t *sp = stile + spos;
+#pragma unroll 4
+			for (uint32_t c4 = 0; c4 < C4; ++c4) sp[c4 * spitch] = tp[c4 * pitch];
 		}
-		__syncthreads();
+		__syncthreads();                                 // the tile has been consumed: refill it under phase 2
+		if (t + gridDim.x < tiles) fetch(t + gridDim.x);
 
-		// column sums over the cluster-contiguous lists
+		// column sums over the cluster-contiguous row ranges
 		for (uint32_t item = tid; item < C4 * nparts; item += R) {
 			const uint32_t c4 = item % C4, part = item / C4;
-			const uint32_t *tc = tile + c4 * pitch;
+			const uint32_t *tc = stile + c4 * spitch;
 			uint32_t seg = 0;
 			for (uint32_t k = 0; k < K; ++k) {
 				const uint32_t end = seg + off[NW * K + k];
-				uint32_t lo = 0, hi = 0;
-				for (uint32_t j = seg + part; j < end; j += nparts) {
-					const uint32_t w = tc[perm[j]];
-					lo += w & 0x00FF00FFu;
-					hi += (w >> 8) & 0x00FF00FFu;
+				uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+				uint32_t j = seg + part;
+				for (; j + 3 * nparts < end; j += 4 * nparts) {
+					const uint32_t w0 = tc[j], w1 = tc[j + nparts], w2 = tc[j + 2 * nparts], w3 = tc[j + 3 * nparts];
+					a0 = __dp4a(w0, 0x00000001u, a0); a1 = __dp4a(w0, 0x00000100u, a1); a2 = __dp4a(w0, 0x00010000u, a2); a3 = __dp4a(w0, 0x01000000u, a3);
+					a0 = __dp4a(w1, 0x00000001u, a0); a1 = __dp4a(w1, 0x00000100u, a1); a2 = __dp4a(w1, 0x00010000u, a2); a3 = __dp4a(w1, 0x01000000u, a3);
+					a0 = __dp4a(w2, 0x00000001u, a0); a1 = __dp4a(w2, 0x00000100u, a1); a2 = __dp4a(w2, 0x00010000u, a2); a3 = __dp4a(w2, 0x01000000u, a3);
+					a0 = __dp4a(w3, 0x00000001u, a0); a1 = __dp4a(w3, 0x00000100u, a1); a2 = __dp4a(w3, 0x00010000u, a2); a3 = __dp4a(w3, 0x01000000u, a3);
 				}
-				if (lo | hi) {
+				for (; j < end; j += nparts) {
+					const uint32_t w0 = tc[j];
+					a0 = __dp4a(w0, 0x00000001u, a0); a1 = __dp4a(w0, 0x00000100u, a1); a2 = __dp4a(w0, 0x00010000u, a2); a3 = __dp4a(w0, 0x01000000u, a3);
+				}
+				if (a0 | a1 | a2 | a3) {
 					uint32_t *a = acc + (k * C4 + c4) * 4;
-					atomicAdd(a + 0, lo & 0xFFFFu);
-					atomicAdd(a + 1, hi & 0xFFFFu);
-					atomicAdd(a + 2, lo >> 16);
-					atomicAdd(a + 3, hi >> 16);
+					atomicAdd(a + 0, a0);
+					atomicAdd(a + 1, a1);
+					atomicAdd(a + 2, a2);
+					atomicAdd(a + 3, a3);
 				}
 				seg = end;
 			}
 		}
-		__syncthreads();
+		__syncthreads();                                 // stile and off are reused by the next tile
 	}
 	for (uint32_t i = tid; i < K * C4 * 4; i += R) {
 		const uint32_t k = i / (C4 * 4), c = i - k * C4 * 4;
@@ -255,9 +313,9 @@ qvz_kmeans_update_kernel(uint32_t K, uint32_t C, uint32_t C4, const unsigned lon
 }
 
 static size_t assign_smem(uint32_t K, uint32_t C4, uint32_t R) {
-	const uint32_t NW = R / 32;
-	size_t words = (size_t) K * C4 + 2 * K + (size_t) K * C4 * 4 + (NW + 1) * K + 1;
-	words += (R + (R & 1)) / 2 + (size_t) C4 * (R + 1);
+	const uint32_t NW = R / 32, KP = ((K <= 8 ? K : QVZ_MAX_K) + 3) & ~3u;
+	size_t words = 4 + (size_t) C4 * (R + 4) + (((size_t) C4 * (R + 1) + 3) & ~(size_t) 3) + (size_t) C4 * KP + (size_t) K * C4 * 4 + KP + K + (NW + 2) * K;
+	words += 4;
 	return words * sizeof(uint32_t);
 }
 
@@ -271,8 +329,9 @@ static void launch_assign(qvz_gpu *h, int64_t *sums_dev, unsigned grid, unsigned
 
 int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev) {
 	const uint32_t K = h->km_K, C4 = h->L.C4;
-	unsigned R = 256;
-	while (R > 32 && assign_smem(K, C4, R) > 110 * 1024) R >>= 1;       // keep >= 2 CTAs per SM when possible
+	unsigned R = 128;                                                   // measured: 128-row tiles (3-5 CTAs per SM) beat 256 and 64
+	while (R > 64 && assign_smem(K, C4, R) > 110 * 1024) R >>= 1;       // keep >= 2 CTAs per SM when possible
+	if (const char *e = getenv("QVZ_KM_R")) R = (unsigned) atoi(e);     // tuning knob: 64, 128 or 256
 	const size_t smem = assign_smem(K, C4, R);
 	if (smem > 220 * 1024) QVZ_FAIL(h, QVZ_ERR_UNSUPPORTED, "k-means: K*columns too large for shared memory");
 	const uint64_t blocks = h->L.P / R;
