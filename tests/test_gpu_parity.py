@@ -218,3 +218,80 @@ def test_sharded_equals_whole(gpu, oracle):
     finally:
         for h in hs:
             h.close()
+
+
+def test_prefetched_draws_and_host_reduction_entry_points(gpu, oracle):
+    """qvz_gpu_prefetch_draws (draws generated early on the auxiliary stream) and the host-sum stepping calls
+    (qvz_gpu_kmeans_assign_host / _update_host) give the same bits as the plain calls."""
+    import ctypes as C
+    from qvz_b200.lib import f64p, i64p, u32p
+    n, c, k = 40_003, 61, 3
+    rows = synth_rows(n, c, seed=77).numpy()
+    init = rows[[5, 20_000, 39_999], :c]
+    o = oracle.kmeans(rows, c, init, 4.0)
+    _load(gpu, rows, c)
+    gpu.prefetch_draws(DEBUG_SEED)                     # before the clusters or the tables exist
+    gpu.kmeans_begin(init)
+    sums = np.zeros(k * c + k, np.int64)
+    moved, counts = np.zeros(k), np.zeros(k, np.uint32)
+    iters, loop = 0, True
+    while loop:
+        assert gpu.L.qvz_gpu_kmeans_assign_host(gpu.h, sums.ctypes.data_as(i64p)) == 0
+        assert gpu.L.qvz_gpu_kmeans_update_host(gpu.h, sums.ctypes.data_as(i64p), moved.ctypes.data_as(f64p), counts.ctypes.data_as(u32p)) == 0
+        assert np.array_equal(moved, o["moved"][iters])
+        loop = moved.max() > 4.0
+        iters += 1
+    assert iters == o["iters"] and np.array_equal(counts, o["counts"])
+    ids, means = gpu.kmeans_end()
+    assert np.array_equal(ids, o["ids"]) and np.array_equal(means, o["means"])
+    t = synthetic_tables(k, c, seed=8)
+    q = gpu.quantize(t, DEBUG_SEED, want_qv=True, want_err=True)          # consumes the prefetched draws
+    q2 = gpu.quantize(t, DEBUG_SEED, want_qv=True, want_err=True)         # generates them again
+    r = oracle.quantize(rows, c, o["ids"], t, DEBUG_SEED)
+    for key in ("symbols", "qv", "line_err"):
+        assert np.array_equal(q[key], r[key]) and np.array_equal(q2[key], r[key]), key
+    other = np.random.default_rng(3).integers(0, 2**31, 32, dtype=np.uint32)
+    gpu.prefetch_draws(other)                          # a prefetch for a different seed must not be used
+    q3 = gpu.quantize(t, DEBUG_SEED)
+    assert np.array_equal(q3["symbols"], r["symbols"])
+
+
+def test_cfg_scale_properties(gpu):
+    """A cfg3-shaped run far beyond what the CPU oracle checks in seconds (2M x 150, K = 3, -f 0.5 -d A), verified through
+    size-independent properties: every line is counted exactly once per column, the count tables agree with the
+    cluster sizes, re-running is idempotent, the symbols are valid states of the quantizer the context selects and
+    the host coder accepts the whole stream."""
+    import tempfile
+    import torch
+    from qvz_b200 import hostlib
+    n, c, k = 2_000_000, 150, 3
+    rows = synth_rows(n, c, seed=2024, device="cuda").cpu().numpy()
+    init = rows[[930_886, 636_915, 238_335], :c]
+    _load(gpu, rows, c)
+    km = gpu.kmeans(init, 4.0)
+    assert km["counts"].sum() == n and np.array_equal(np.bincount(km["ids"], minlength=k), km["counts"])
+    counts = gpu.cond_counts()
+    per_col = counts.reshape(k, -1).sum(1)
+    assert np.array_equal(per_col, km["counts"].astype(np.uint64) * c)           # each line once per column, in its cluster
+    assert np.array_equal(counts[:, 0, :].sum(1), km["counts"])                  # column 0 rows
+    assert np.array_equal(gpu.cond_counts(), counts)                             # idempotent
+    km2 = gpu.kmeans(init, 4.0)
+    assert km2["iters"] == km["iters"] and np.array_equal(km2["ids"], km["ids"])
+    cb = hostlib.design_codebooks(counts, c, k, hostlib.MODE_RATIO, 0.5, hostlib.DIST_MANHATTAN)
+    q = gpu.quantize(cb.tables, DEBUG_SEED, want_qv=True, want_err=True)
+    sym, qv = q["symbols"], q["qv"]
+    assert (qv[:, c] == 10).all() and qv[:, :c].min() >= 33 and qv[:, :c].max() < 33 + 72
+    # per-line error == L1 distance between the input and the -u image, divided by the columns (integer matrix: exact)
+    l1 = np.abs(rows[:, :c].astype(np.int32) - qv[:, :c].astype(np.int32)).sum(1)
+    assert np.array_equal(q["line_err"], l1 / float(c))
+    # the state of every symbol indexes the output alphabet of the quantizer its context selects, and decodes to qv
+    kc = km["ids"].astype(np.int64)[:, None] * c + np.arange(c)[None, :]
+    prev = np.concatenate([np.zeros((n, 1), np.int64), qv[:, :c - 1].astype(np.int64) - 33], axis=1)
+    ctx = cb.ctx_of.reshape(-1, 72)[kc, prev]
+    assert (ctx != 0xFF).all()
+    qi = cb.q_off[kc].astype(np.int64) + 2 * ctx + (sym >> 7)
+    assert np.array_equal(cb.smap.reshape(-1, 72)[qi, qv[:, :c].astype(np.int64) - 33], sym & 0x7F)
+    assert np.array_equal(cb.qmap.reshape(-1, 72)[qi, rows[:, :c].astype(np.int64) - 33], qv[:, :c] - 33)
+    with tempfile.TemporaryDirectory() as d:
+        nbytes = cb.encode(d + "/big.qvz", km["ids"], sym, DEBUG_SEED)           # the coder walks the same contexts and accepts every symbol
+    assert 0 < nbytes < n * c
