@@ -201,7 +201,8 @@ def run_native(args):
         sampler.start()
     h.reset_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {"kmeans_ms": 0.0, "kmeans_assign_ms": 0.0, "cond_counts_ms": 0.0, "quantize_ms": 0.0, "quantize_setup_ms": 0.0}
+    stage = {"kmeans_ms": 0.0, "kmeans_assign_ms": 0.0, "cond_counts_ms": 0.0, "quantize_ms": 0.0, "quantize_draws_ms": 0.0,
+             "quantize_setup_ms": 0.0}
     ev0.record(stream)
     for _ in range(args.steps):
         tm = step_resident()
@@ -247,18 +248,25 @@ def run_native(args):
     except OSError:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    # dominant kernel = the one with the largest share of the step
+    # per-kernel durations (CUDA events on the library's streams, averaged over the timed steps) and algorithmic bytes
+    # (1 B per QV read, 1 B per cluster id, 1 B per emitted symbol; the WELL draws are an
+    # intermediate, not algorithmic I/O -- the draw generator's time is shown but it has no roofline of its own)
+    walk_ms = stage["quantize_ms"] - stage["quantize_draws_ms"]
     kern = {"kmeans_assign": (stage["kmeans_assign_ms"] / max(iters, 1), sym_per_rank + n),
             "cond_counts": (stage["cond_counts_ms"], sym_per_rank + n),
-            "quantize": (stage["quantize_ms"], 2 * sym_per_rank + n)}
-    share = {"kmeans_assign": stage["kmeans_assign_ms"], "cond_counts": stage["cond_counts_ms"], "quantize": stage["quantize_ms"]}
-    dom = max(share, key=share.get)
+            "quantize_walk": (walk_ms, 2 * sym_per_rank + n)}
+    share = {"kmeans_assign": stage["kmeans_assign_ms"], "cond_counts": stage["cond_counts_ms"], "quantize_walk": walk_ms}
+    dom = max(share, key=share.get)                # dominant kernel = largest share of the step
     dur_ms, alg_bytes = kern[dom]
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+    names = {"kmeans_assign": "qvz_kmeans_single_kernel" if k == 1 else "qvz_kmeans_assign_kernel", "cond_counts": "qvz_cond_counts_kernel",
+             "quantize_walk": "qvz_quantize_batched_kernel"}
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": ncu_traffic(dom, cfg),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "per_kernel_GBps": {kk: round(b / (d * 1e-3) / 1e9, 1) for kk, (d, b) in kern.items() if d > 0},
+                "per_kernel_GBps": {names[kk]: round(b / (d * 1e-3) / 1e9, 1) for kk, (d, b) in kern.items() if d > 0},
+                "per_kernel_ms": {**{names[kk]: round(d, 4) for kk, (d, b) in kern.items()}, "qvz_draws_kernel": round(stage["quantize_draws_ms"], 4)},
+                "quantize_stage_GBps_incl_draw_generator": round((2 * sym_per_rank + n) / (stage["quantize_ms"] * 1e-3) / 1e9, 1),
                 "algorithmic_bytes_per_launch": alg_bytes}
 
     cpu = cpu_baseline(cfg, args) if world == 1 and not args.no_cpu else None
@@ -292,7 +300,7 @@ def ncu_traffic(kernel, cfg):
     if not files:
         return None
     per = json.load(open(files[-1]))["dram_bytes_per_launch"]
-    pick = {"quantize": ("qvz_draws_kernel", "qvz_quantize_batched_kernel"), "cond_counts": ("qvz_cond_counts_kernel",),
+    pick = {"quantize_walk": ("qvz_quantize_batched_kernel",), "cond_counts": ("qvz_cond_counts_kernel",),
             "kmeans_assign": ("qvz_kmeans_single_kernel", "qvz_kmeans_assign_kernel")}[kernel]
     tot = sum(v for k, v in per.items() if any(p in k for p in pick))
     return int(tot) if tot else None

@@ -540,10 +540,12 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 		}
 		if (tid == 0) stage(0, gcount);
 		uint32_t xn[QB_LPT], dn[QB_LPT];
+		const uint32_t *xr = Xw + pbase, *drw = Dw + pbase;      // running pointers: one word column (P slots) per step
+		uint32_t *yr = Yw + pbase, *qr = WANT_QV ? Qw + pbase : nullptr;
 #pragma unroll
 		for (int j = 0; j < QB_LPT; ++j) {
-			xn[j] = ld_stream_u32(Xw + pbase + j * QB_THREADS);
-			dn[j] = ld_stream_u32(Dw + pbase + j * QB_THREADS);
+			xn[j] = ld_stream_u32(xr + j * QB_THREADS);
+			dn[j] = ld_stream_u32(drw + j * QB_THREADS);
 		}
 		// one data word (4 columns) of the QB_LPT lines of this thread; TAIL = the last, partial word
 		auto word = [&](uint32_t c4, auto tail_tag) {
@@ -551,13 +553,16 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			uint32_t x[QB_LPT], dr[QB_LPT], outw[QB_LPT], qvw[QB_LPT];
 #pragma unroll
 			for (int j = 0; j < QB_LPT; ++j) {
-				x[j] = valid[j] ? xn[j] - 0x21212121u : 0u;
+				// raw ASCII bytes index the tables directly: the -33 is folded into the table base below.  A slot without
+				// a line (zero words) walks symbol 0 so that every lookup stays inside the tables; nothing of it is kept.
+				x[j] = valid[j] ? xn[j] : 0x21212121u;
 				dr[j] = dn[j];
 				outw[j] = 0;
 				qvw[j] = 0;
 			}
 			if (!TAIL) {                                 // next word's rows and draws: in flight during this word
-				const uint32_t *xr = Xw + (uint64_t) (c4 + 1) * L.P + pbase, *drw = Dw + (uint64_t) (c4 + 1) * L.P + pbase;
+				xr += L.P;
+				drw += L.P;
 #pragma unroll
 				for (int j = 0; j < QB_LPT; ++j) {
 					xn[j] = ld_stream_u32(xr + j * QB_THREADS);
@@ -577,7 +582,7 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 					for (int sidx = 0; sidx < S; ++sidx) {
 						const int b = g * S + sidx;
 						if (!TAIL || col0 + sidx < C) {
-							const uint32_t tab = tabg + sidx * col_bytes;
+							const uint32_t tab = tabg + sidx * col_bytes - 33u * 4u;       // indexed by the raw byte ('!' + value)
 #pragma unroll
 							for (int j = 0; j < QB_LPT; ++j) {
 								// draw >= qratio  <=>  (int)(draw << 24) > (int)((qratio-1) << 24 | low bits of the previous variant)
@@ -591,9 +596,9 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 								const uint32_t didx = __byte_perm(v, 0, 0x4441);
 								if (DMODE == 2) erri[j] += lds_u32(dd_addr + didx * 4);
 								else if (DMODE == 1) errd[j] += lds_f64(dd_addr + didx * 8);
-								else {
-									if (didx == QB_POISON) missing |= valid[j];
-									errd[j] += __ldg(&D[data + 72u * (v & 0x7Fu)]);
+								else if (valid[j]) {
+									if (didx == QB_POISON) missing = true;
+									errd[j] += __ldg(&D[(data - 33u) + 72u * (v & 0x7Fu)]);
 								}
 								vprev[j] = v;
 							}
@@ -601,13 +606,13 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 					}
 				}
 			}
-			uint32_t *yr = Yw + (uint64_t) c4 * L.P + pbase;
 #pragma unroll
 			for (int j = 0; j < QB_LPT; ++j) st_stream_u32(yr + j * QB_THREADS, outw[j]);
+			yr += L.P;
 			if (WANT_QV) {
-				uint32_t *qr = Qw + (uint64_t) c4 * L.P + pbase;
 #pragma unroll
 				for (int j = 0; j < QB_LPT; ++j) st_stream_u32(qr + j * QB_THREADS, (qvw[j] & 0x7F7F7F7Fu) + 0x21212121u);
+				qr += L.P;
 			}
 		};
 		for (uint32_t c4 = 0; c4 + 1 < C4; ++c4) word(c4, std::false_type{});

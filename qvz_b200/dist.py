@@ -68,12 +68,18 @@ class ShardedFrontEnd:
         self._sums = None
         self._counts = None
         self.allreduce_calls = 0
+        self._ext = None                                       # the library's stream as a torch stream (built once)
         self.kmeans_ms = self.kmeans_assign_ms = 0.0           # device time of the last kmeans() (CUDA events, lib stream)
 
     # the library works on its own stream: run the collective on that stream so no host sync is needed
+    def _lib_stream(self):
+        if self._ext is None:
+            self._ext = torch.cuda.ExternalStream(self.h.stream, device=self.device)
+        return self._ext
+
     def _on_lib_stream(self):
         if self.device.type == "cuda":
-            return torch.cuda.stream(torch.cuda.ExternalStream(self.h.stream, device=self.device))
+            return torch.cuda.stream(self._lib_stream())
         import contextlib
         return contextlib.nullcontext()
 
@@ -120,7 +126,7 @@ class ShardedFrontEnd:
         cuda = self.device.type == "cuda"
         ev = []
         if cuda:
-            ext = torch.cuda.ExternalStream(h.stream, device=self.device)
+            ext = self._lib_stream()
         while iters < max_iter and loop:                       # src/cluster.c:221
             if cuda:
                 ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
