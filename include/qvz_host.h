@@ -59,6 +59,10 @@ int qvz_host_write_codebooks(const qvz_codebooks *cb, uint64_t n_lines, uint8_t 
 int qvz_host_encode(const qvz_codebooks *cb, const char *path, uint64_t n_lines, const uint8_t *cluster_ids,
                     const uint8_t *symbols, const uint32_t well_seed[32], uint64_t *stream_bytes_out);
 
+/* decode() (src/main.c:132-160): read_codebooks + start_qv_decompression: writes the quantized lines of a .qvz file
+ * (what `-u` dumped at encode time).  Returns 0, -1 on I/O errors, -2 on a malformed file. */
+int qvz_host_decode(const char *in_path, const char *out_path, uint64_t *lines_out);
+
 #ifdef __cplusplus
 }
 #endif

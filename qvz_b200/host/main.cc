@@ -381,12 +381,19 @@ int main(int argc, char **argv) {
 			printf("Compression will use %d clusters, with a movement threshold of %.0f.\n", opts.clusters, opts.cluster_threshold);
 		}
 	}
-	if (extract) {
-		// The decoder (src/qv_compressor.c:145-231) is one sequential arithmetic-decoding chain: it is outside the
-		// data-parallel front end this program accelerates, and the container is unchanged, so the reference's own
-		// `qvz -x` decodes these files (tests/test_cli_gpu.py does exactly that).
-		printf("-x: decoding is not part of the B200 front end; the .qvz container is unchanged, use the reference qvz -x.\n");
-		return 2;
+	if (extract) {                                   // decode() (src/main.c:132-160): sequential host work
+		const double t0 = now();
+		uint64_t lines = 0;
+		const int rc = qvz_host_decode(input_name, output_name, &lines);
+		if (rc == -1) {
+			perror("Unable to open input or output files");
+			exit(1);
+		} else if (rc) {
+			printf("%s is not a valid qvz file.\n", input_name);
+			exit(1);
+		}
+		if (opts.verbose) printf("Decoded %llu lines in %f seconds.\n", (unsigned long long) lines, now() - t0);
+		return 0;
 	}
 	encode(input_name, output_name, &opts);
 	return 0;

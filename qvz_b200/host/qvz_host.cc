@@ -623,3 +623,255 @@ extern "C" int qvz_host_encode(const qvz_codebooks *cb, const char *path, uint64
 	if (fclose(fp) != 0 && !rc) rc = -1;
 	return rc;
 }
+
+// ------------------------------------------------------------------------------------------------------ decoder
+// decode() (src/main.c:132-160): read_codebooks (src/codebook.c:560-669) + start_qv_decompression
+// (src/qv_compressor.c:145-231) with the arithmetic decoder of src/arith.c:118-205.  One sequential chain of
+// adaptive-coder steps: host work by nature; here so that the command line is complete (qvz -x).
+namespace {
+
+struct BitReader {                                   // stream_read_bit (src/os_stream.c:35-51); zeros past the end of the file
+	std::vector<uint8_t> buf;
+	size_t pos = 0;
+	uint32_t bit = 0;
+	inline uint32_t next() {
+		uint32_t v = 0;
+		if (pos < buf.size()) v = (buf[pos] >> (7 - bit)) & 1u;
+		if (++bit == 8) {
+			bit = 0;
+			++pos;
+		}
+		return v;
+	}
+};
+
+struct Decoder {
+	static constexpr uint32_t M = 22, MSB = M - 1, SMSB = M - 2, CLEAR = (1u << MSB) - 1, R = 1u << (M - 3), STEP = 8;
+	uint32_t l = 0, u = (1u << M) - 1, t = 0;
+	BitReader &is;
+	explicit Decoder(BitReader &r) : is(r) {
+		for (int b = (int) M - 1; b >= 0; --b) t |= is.next() << b;       // a->t = stream_read_bits(os, m) (src/qv_stream.c:113)
+	}
+	static void update(Stats &s, uint32_t x) {                              // update_stats (src/qv_stream.c:9-25)
+		s.counts[x] += STEP;
+		s.n += STEP;
+		if (s.n > R) {
+			s.n = 0;
+			for (uint32_t i = 0; i < s.card; ++i)
+				if (s.counts[i]) {
+					s.counts[i] >>= 1;
+					s.counts[i] += 1;
+					s.n += s.counts[i];
+				}
+		}
+	}
+	inline uint32_t symbol(const Stats &s) const {                           // the search shared by both decoder steps
+		const uint64_t range = (uint64_t) (u - l + 1), gap = (uint64_t) (t - l + 1);
+		const uint32_t sub = (uint32_t) ((gap * s.n - 1) / range);
+		uint32_t k = 0, cum = 0;
+		while (sub >= cum) cum += s.counts[k++];
+		return k - 1;
+	}
+	inline uint32_t step(Stats &s) {                                         // arithmetic_decoder_step (src/arith.c:118-188)
+		const uint64_t range = (uint64_t) (u - l + 1);
+		const uint32_t x = symbol(s);
+		uint32_t below = 0;
+		for (uint32_t i = 0; i < x; ++i) below += s.counts[i];
+		const uint32_t upto = below + s.counts[x];
+		u = l + (uint32_t) ((range * upto) / s.n) - 1;
+		l = l + (uint32_t) ((range * below) / s.n);
+		for (;;) {
+			if ((l >> MSB) == (u >> MSB)) {
+				l = (l & CLEAR) << 1;
+				u = ((u & CLEAR) << 1) + 1;
+				t = ((t & CLEAR) << 1) + is.next();
+			} else if ((l >> SMSB) == 0x01 && (u >> SMSB) == 0x02) {
+				l = (l << 1) & CLEAR;
+				u = (((u << 1) & CLEAR) | (1u << MSB)) + 1;
+				t = (((t & CLEAR) << 1) ^ (1u << MSB)) + is.next();
+			} else break;
+		}
+		update(s, x);
+		return x;
+	}
+};
+
+// well_1024a + well_1024a_bits(7) (src/well.c:8-46)
+struct Well {
+	uint32_t s[32], n = 0, out = 0, left = 0;
+	inline uint32_t word() {
+		const uint32_t z0 = s[(n + 31) & 31], a = s[(n + 3) & 31], b = s[(n + 24) & 31], c = s[(n + 10) & 31];
+		const uint32_t z1 = s[n] ^ (a ^ (a >> 8));
+		const uint32_t z2 = (b ^ (b << 19)) ^ (c ^ (c << 14));
+		s[n] = z1 ^ z2;
+		n = (n + 31) & 31;
+		s[n] = (z0 ^ (z0 << 11)) ^ (z1 ^ (z1 << 7)) ^ (z2 ^ (z2 << 13));
+		return s[n];
+	}
+	inline uint32_t draw7() {
+		if (left < 7) {
+			out = word();
+			left = 32;
+		}
+		const uint32_t r = out & 127u;
+		out >>= 7;
+		left -= 7;
+		return r;
+	}
+};
+
+// find_output_alphabet (src/quantizer.c:167-191): the decoder rebuilds output alphabets from runs of equal values
+void find_output_alphabet(Quantizer &Q) {
+	Q.out.sym.clear();
+	uint8_t p = Q.q[0];
+	Q.out.sym.push_back(p);
+	for (uint32_t x = 1; x < A; ++x)
+		if (Q.q[x] != p) {
+			p = Q.q[x];
+			Q.out.sym.push_back(p);
+		}
+	Q.out.reindex();
+}
+
+}  // namespace
+
+extern "C" int qvz_host_decode(const char *in_path, const char *out_path, uint64_t *lines_out) {
+	if (!in_path || !out_path) return -1;
+	FILE *fin = fopen(in_path, "rb");
+	if (!fin) return -1;
+	std::vector<uint8_t> file;
+	{
+		fseek(fin, 0, SEEK_END);
+		const long sz = ftell(fin);
+		fseek(fin, 0, SEEK_SET);
+		file.resize(sz > 0 ? (size_t) sz : 0);
+		if (!file.empty() && fread(file.data(), 1, file.size(), fin) != file.size()) {
+			fclose(fin);
+			return -1;
+		}
+		fclose(fin);
+	}
+	size_t pos = 0;
+	auto need = [&](size_t n) { return pos + n <= file.size(); };
+	if (!need(9)) return -2;
+	const uint32_t K = file[0];                      // read_codebooks (src/codebook.c:560-581): big-endian columns and lines
+	const uint32_t C = (uint32_t) file[1] << 24 | (uint32_t) file[2] << 16 | (uint32_t) file[3] << 8 | file[4];
+	const uint32_t lines = (uint32_t) file[5] << 24 | (uint32_t) file[6] << 16 | (uint32_t) file[7] << 8 | file[8];
+	pos = 9;
+	if (K == 0 || C == 0 || C > QVZ_MAX_COLUMNS) return -2;
+	std::vector<ClusterBook> books(K);
+	auto read_q = [&](Quantizer &Q) -> bool {        // COPY_Q_FROM_LINE (include/codebook.h:102)
+		if (!need(A)) return false;
+		for (uint32_t i = 0; i < A; ++i) {
+			Q.q[i] = (uint8_t) (file[pos + i] - 33);
+			if (Q.q[i] >= A) return false;
+		}
+		pos += A;
+		find_output_alphabet(Q);
+		return true;
+	};
+	auto eol = [&]() -> bool {                       // every codebook line ends with one '\n'
+		if (!need(1) || file[pos] != '\n') return false;
+		++pos;
+		return true;
+	};
+	for (uint32_t k = 0; k < K; ++k) {               // read_codebook (src/codebook.c:586-669)
+		ClusterBook &B = books[k];
+		B.in.resize(C);
+		B.q.resize(C);
+		B.qratio.resize(C);
+		B.in[0].sym.assign(1, 0);
+		B.in[0].reindex();
+		B.q[0].resize(2);
+		B.qratio[0].resize(1);
+		if (!need(2)) return -2;
+		B.qratio[0][0] = (uint8_t) (file[pos] - 33);
+		++pos;
+		if (!eol() || !read_q(B.q[0][0]) || !eol() || !read_q(B.q[0][1]) || !eol()) return -2;
+		Alphabet uniques = alphabet_union(B.q[0][0].out, B.q[0][1].out);
+		for (uint32_t c = 1; c < C; ++c) {
+			B.in[c] = uniques;
+			const size_t nc = uniques.sym.size();
+			B.q[c].resize(2 * nc);
+			B.qratio[c].resize(nc);
+			if (!need(nc)) return -2;
+			for (size_t i = 0; i < nc; ++i) B.qratio[c][i] = (uint8_t) (file[pos + i] - 33);
+			pos += nc;
+			if (!eol()) return -2;
+			Alphabet next;
+			next.reindex();
+			for (int hi = 0; hi < 2; ++hi) {
+				for (size_t i = 0; i < nc; ++i) {
+					if (!read_q(B.q[c][2 * i + hi])) return -2;
+					next = alphabet_union(next, B.q[c][2 * i + hi].out);
+				}
+				if (!eol()) return -2;
+			}
+			uniques = next;
+		}
+	}
+	if (!need(128)) return -2;
+	Well well;                                       // initialize_arithStream, decompressor side (src/qv_stream.c:72-74, 93)
+	memcpy(well.s, &file[pos], 128);
+	pos += 128;
+	BitReader is;
+	is.buf.assign(file.begin() + pos, file.end());
+
+	// adaptive models, exactly as the encoder sets them up but from the decoder's output alphabets
+	std::vector<std::vector<std::vector<std::vector<uint32_t>>>> cnt(K);
+	std::vector<std::vector<std::vector<Stats>>> st(K);
+	for (uint32_t k = 0; k < K; ++k) {
+		cnt[k].resize(C);
+		st[k].resize(C);
+		for (uint32_t c = 0; c < C; ++c) {
+			const size_t nqc = books[k].q[c].size();
+			cnt[k][c].resize(nqc);
+			st[k][c].resize(nqc);
+			for (size_t j = 0; j < nqc; ++j) {
+				const uint32_t card = (uint32_t) books[k].q[c][j].out.sym.size();
+				cnt[k][c][j].assign(card, 1u);
+				st[k][c][j] = Stats{cnt[k][c][j].data(), card, card};
+			}
+		}
+	}
+	std::vector<uint32_t> ccounts(K, 1u);
+	Stats cstats{ccounts.data(), K, K};
+
+	FILE *fout = fopen(out_path, "wt");
+	if (!fout) return -1;
+	Decoder dec(is);
+	std::vector<uint8_t> line(C + 1);
+	line[C] = '\n';
+	int rc = 0;
+	for (uint64_t ln = 0; ln < lines && !rc; ++ln) {
+		const uint32_t k = dec.step(cstats);                                 // qv_read_cluster
+		if (k >= K) {
+			rc = -2;
+			break;
+		}
+		const ClusterBook &B = books[k];
+		uint32_t prev = 0;
+		for (uint32_t c = 0; c < C; ++c) {
+			const uint32_t ctx = B.in[c].idx[prev];                          // choose_quantizer (src/codebook.c:162-171)
+			if (ctx == NOT_FOUND) {
+				rc = -2;
+				break;
+			}
+			const uint32_t qi = 2 * ctx + (well.draw7() >= B.qratio[c][ctx] ? 1u : 0u);
+			Stats &s = st[k][c][qi];
+			uint32_t state;
+			if (ln + 1 == lines && c + 1 == C) state = dec.symbol(s);        // decoder_last_step (src/arith.c:190-205): no more bits are read
+			else state = dec.step(s);
+			if (state >= s.card) {
+				rc = -2;
+				break;
+			}
+			prev = B.q[c][qi].out.sym[state];
+			line[c] = (uint8_t) (prev + 33);
+		}
+		if (!rc && fwrite(line.data(), 1, C + 1, fout) != C + 1) rc = -1;
+	}
+	if (fclose(fout) != 0 && !rc) rc = -1;
+	if (lines_out) *lines_out = lines;
+	return rc;
+}

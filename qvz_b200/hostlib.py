@@ -17,7 +17,7 @@ MODE_RATIO, MODE_FIXED = 0, 1
 DIST_MANHATTAN, DIST_MSE, DIST_LORENTZ = 1, 2, 3
 
 EXPORTS = ["qvz_host_distortion", "qvz_host_distortion_file", "qvz_host_design", "qvz_host_free", "qvz_host_tables",
-           "qvz_host_codebook_bytes", "qvz_host_write_codebooks", "qvz_host_encode"]
+           "qvz_host_codebook_bytes", "qvz_host_write_codebooks", "qvz_host_encode", "qvz_host_decode"]
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -60,6 +60,8 @@ def load() -> C.CDLL:
         L.qvz_host_write_codebooks.argtypes = [C.c_void_p, C.c_uint64, u8p]
         L.qvz_host_encode.restype = C.c_int
         L.qvz_host_encode.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, u8p, u8p, u32p, C.POINTER(C.c_uint64)]
+        L.qvz_host_decode.restype = C.c_int
+        L.qvz_host_decode.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -125,6 +127,15 @@ class Codebooks:
             self.h = None
 
     __del__ = close
+
+
+def decode_file(src: str, dst: str) -> int:
+    """qvz -x: returns the number of lines written."""
+    n = C.c_uint64(0)
+    rc = load().qvz_host_decode(src.encode(), dst.encode(), C.byref(n))
+    if rc:
+        raise RuntimeError(f"qvz_host_decode failed ({rc})")
+    return n.value
 
 
 def design_codebooks(counts, columns, clusters, mode, target, distortion, threads: int = 0) -> Codebooks:

@@ -73,6 +73,11 @@ def test_cli_vs_reference_binary(tmp_path, n, c, flags, gpus):
     r = _run(REF, ["-x", str(tmp_path / "new.qvz"), dec])
     assert r.returncode == 0
     assert np.array_equal(np.fromfile(dec, np.uint8), out["new"][1])
+    # ... and the new command line's -x decodes the REFERENCE's file to the same lines
+    dec2 = str(tmp_path / "dec2.txt")
+    r = _run(CLI, ["-x", str(tmp_path / "ref.qvz"), dec2])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert np.array_equal(np.fromfile(dec2, np.uint8), out["ref"][1])
 
 
 def test_cli_errors(tmp_path):

@@ -93,3 +93,18 @@ def test_design_and_file_vs_compiled_reference(ref, tmp_path, n, c, k, mode, rat
     mine = str(tmp_path / "mine.qvz")
     cb.encode(mine, ids, q["symbols"], DEBUG_SEED)
     assert np.array_equal(np.fromfile(mine, np.uint8), np.fromfile(dst, np.uint8))
+
+
+def test_decode_reproduces_u_dump(golden, tmp_path):
+    """qvz -x on the reference's own .qvz file gives the reference's -u dump (the reference's test.sh criterion)."""
+    src, dst = str(tmp_path / "in.qvz"), str(tmp_path / "out.txt")
+    golden["qvz"].tofile(src)
+    assert hostlib.decode_file(src, dst) == golden["rows"].shape[0]
+    assert np.array_equal(np.fromfile(dst, np.uint8).reshape(golden["qv"].shape), golden["qv"])
+
+
+def test_decode_rejects_garbage(tmp_path):
+    src = str(tmp_path / "bad.qvz")
+    np.arange(200, dtype=np.uint8).tofile(src)
+    with pytest.raises(RuntimeError):
+        hostlib.decode_file(src, str(tmp_path / "o.txt"))
