@@ -171,6 +171,8 @@ def run_native(args):
             torch.cuda.synchronize()
 
     def step_resident():
+        if args.prefetch:
+            h.prefetch_draws(seed)                 # the draws depend on the seed only: generated under k-means
         if fe:
             fe.kmeans(init, cfg.get("threshold", 4.0), want_ids=False)
             fe.cond_counts(want_host=False)
@@ -414,6 +416,7 @@ def main():
     ap.add_argument("--lines", type=int, default=0, help="override lines per GPU (parity/dev runs)")
     ap.add_argument("--cpu-lines", type=int, default=1_000_000, help="lines in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--prefetch", type=int, default=0, help="1: start the WELL draw generation at the start of the step (overlaps k-means)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

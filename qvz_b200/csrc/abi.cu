@@ -192,7 +192,11 @@ extern "C" int qvz_gpu_open(qvz_gpu **out, int device) {
 	QVZ_CUDA(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
 	QVZ_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 	QVZ_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-	QVZ_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+	{                                            // the draw generator is issue-bound: at high priority it shares the SMs with the
+		int lo = 0, hi = 0;                      // memory-bound stages it overlaps instead of queueing behind their CTAs
+		QVZ_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		QVZ_CUDA(h, cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi));
+	}
 	QVZ_CUDA(h, cudaEventCreate(&h->ev_draws_start));
 	QVZ_CUDA(h, cudaEventCreate(&h->ev_draws));
 	QVZ_CUDA(h, cudaEventCreate(&h->ev_jump_done));
