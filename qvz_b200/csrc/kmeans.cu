@@ -158,10 +158,16 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
 		{                                                // scatter this row to its sorted position
 			uint32_t spos = off[warp * K + key] + rank;
 			for (uint32_t k = 0; k < key; ++k) spos += off[NW * K + k];
-			const uint32_t *tp = tile + tid;
-			uint32_t *sp = stile + spos;
+			uint32_t src = km_smem_u32(tile + tid), dst = km_smem_u32(stile + spos);
+			const uint32_t sstep = pitch * 4, dstep = spitch * 4;
 #pragma unroll 4
-			for (uint32_t c4 = 0; c4 < C4; ++c4) sp[c4 * spitch] = tp[c4 * pitch];
+			for (uint32_t c4 = 0; c4 < C4; ++c4) {           // explicit shared addresses: 4 instructions per word
+				uint32_t w;
+				asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(src));
+				asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst), "r"(w) : "memory");
+				src += sstep;
+				dst += dstep;
+			}
 		}
 		__syncthreads();                                 // the tile has been consumed: refill it under phase 2
 		if (t + gridDim.x < tiles) fetch(t + gridDim.x);

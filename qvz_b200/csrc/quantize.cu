@@ -462,11 +462,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, u
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
-	uint2 v;
-	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-	return v;
-}
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
 	double v;
 	asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
