@@ -103,6 +103,22 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this rank on the CPUs closest to its GPU (NVML's CPU affinity), so that its pinned host buffers are
+    first-touched on that NUMA node and the H2D/D2H copies of the e2e leg do not cross sockets.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(gpu_index), (os.cpu_count() + 63) // 64)
+        near = {i for i in range(os.cpu_count()) if (mask[i // 64] >> (i % 64)) & 1} & os.sched_getaffinity(0)
+        if near:
+            os.sched_setaffinity(0, near)
+            return len(near)
+    except Exception as e:                         # no NVML, restricted cgroup, ...: keep the default placement
+        log(f"[gpu {gpu_index}] NUMA binding skipped: {e!r}")
+    return 0
+
+
 # ------------------------------------------------------------------------------------------ native arm
 def run_native(args):
     import torch
@@ -115,6 +131,7 @@ def run_native(args):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
+        bind_to_gpu_numa_node(local)               # before any pinned allocation: first touch decides the NUMA node
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = workload(args, world)
     n, c, k = cfg["lines"], cfg["columns"], cfg["clusters"]
