@@ -87,3 +87,25 @@ def test_cli_errors(tmp_path):
     assert r.returncode == 1 and "load_file returned error" in r.stdout
     r = _run(CLI, ["-h"])
     assert r.returncode == 0 and r.stdout.startswith("Usage:")
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/qvz_ref_det not built")
+def test_cfg1_full_size_vs_reference_binary(tmp_path):
+    """BASELINE.json configs[0] at its full size: `qvz -q -f 1.0 -d M -c 1` on 1M synthetic 100-bp lines -- the one
+    config the reference itself finishes in about a minute.  Same .qvz bytes, same -u dump, same -s numbers."""
+    n, c = 1_000_000, 100
+    rows = synth_rows(n, c, seed=1234, device="cuda").cpu().numpy()
+    src = str(tmp_path / "cfg1.txt")
+    rows.tofile(src)
+    flags = ["-q", "-f", "1.0", "-d", "M", "-c", "1"]
+    out = {}
+    for tag, exe, env in (("ref", REF, {}), ("new", CLI, {"QVZ_DEBUG_SEED": "1"})):
+        dst, uf = str(tmp_path / f"{tag}.qvz"), str(tmp_path / f"{tag}.u")
+        r = _run(exe, flags + ["-u", uf, "-s", src, dst], env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        out[tag] = (np.fromfile(dst, np.uint8), np.fromfile(uf, np.uint8), r.stdout)
+    assert np.array_equal(out["new"][1], out["ref"][1]), "-u dump differs"
+    assert out["new"][0].size == out["ref"][0].size and np.array_equal(out["new"][0], out["ref"][0]), ".qvz differs"
+    f_new, f_ref = out["new"][2].split(","), out["ref"][2].split(",")
+    assert [f_new[i].strip() for i in (1, 3, 7)] == [f_ref[i].strip() for i in (1, 3, 7)]
+    assert float(f_new[5]) < float(f_ref[5])          # wall time of the whole command, reference vs new

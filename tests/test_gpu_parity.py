@@ -295,3 +295,18 @@ def test_cfg_scale_properties(gpu):
     with tempfile.TemporaryDirectory() as d:
         nbytes = cb.encode(d + "/big.qvz", km["ids"], sym, DEBUG_SEED)           # the coder walks the same contexts and accepts every symbol
     assert 0 < nbytes < n * c
+
+
+def test_quantize_custom_distortion_matrix(gpu, oracle):
+    """-D FILE: an arbitrary (non-Toeplitz, non-integer) 72x72 matrix takes the general distortion path of both walks."""
+    n, c, k = 9_000, 47, 2
+    rows = synth_rows(n, c, seed=314).numpy()
+    ids = np.random.default_rng(2).integers(0, k, n, dtype=np.uint8)
+    t = synthetic_tables(k, c, seed=21)
+    t.distortion = np.random.default_rng(5).random(72 * 72) * 9.0
+    _load(gpu, rows, c)
+    gpu.set_clusters(k, ids)
+    q = _quantize_both_paths(gpu, t, DEBUG_SEED)
+    o = oracle.quantize(rows, c, ids, t, DEBUG_SEED)
+    assert np.array_equal(q["symbols"], o["symbols"]) and np.array_equal(q["qv"], o["qv"])
+    assert np.array_equal(q["line_err"], o["line_err"])

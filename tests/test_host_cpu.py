@@ -108,3 +108,19 @@ def test_decode_rejects_garbage(tmp_path):
     np.arange(200, dtype=np.uint8).tofile(src)
     with pytest.raises(RuntimeError):
         hostlib.decode_file(src, str(tmp_path / "o.txt"))
+
+
+def test_custom_distortion_file(tmp_path):
+    """-D FILE (gen_custom_distortion, src/distortion.c:100-145): row x of the file is D[x + 72*y] for y = 0..71."""
+    import ctypes as C
+    m = np.round(np.random.default_rng(9).random((72, 72)) * 5, 3)       # short fields: the reference reads rows through a 1024-byte buffer
+    path = tmp_path / "dist.csv"
+    with open(path, "w") as f:
+        f.write("# comment line\n")
+        for x in range(72):
+            f.write(",".join(repr(float(v)) for v in m[x]) + "\n")
+    out = np.zeros(72 * 72, np.float64)
+    L = hostlib.load()
+    assert L.qvz_host_distortion_file(str(path).encode(), out.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    assert np.array_equal(out.reshape(72, 72), m.T)                       # index x + 72*y
+    assert L.qvz_host_distortion_file(b"/nonexistent/file", out.ctypes.data_as(C.POINTER(C.c_double))) == -1
