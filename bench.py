@@ -271,7 +271,8 @@ def run_native(args):
     # (1 B per QV read, 1 B per cluster id, 1 B per emitted symbol; the WELL draws are an
     # intermediate, not algorithmic I/O -- the draw generator's time is shown but it has no roofline of its own)
     walk_ms = stage["quantize_ms"] - stage["quantize_draws_ms"]
-    kern = {"kmeans_assign": (stage["kmeans_assign_ms"] / max(iters, 1), sym_per_rank + n),
+    km_launches = 1 if k == 1 else max(iters, 1)   # K = 1: the rows are read once per run, later iterations reuse the sums
+    kern = {"kmeans_assign": (stage["kmeans_assign_ms"] / km_launches, sym_per_rank + n),
             "cond_counts": (stage["cond_counts_ms"], sym_per_rank + n),
             "quantize_walk": (walk_ms, 2 * sym_per_rank + n)}
     share = {"kmeans_assign": stage["kmeans_assign_ms"], "cond_counts": stage["cond_counts_ms"], "quantize_walk": walk_ms}

@@ -152,6 +152,7 @@ static void release_kmeans(qvz_gpu *h) {
 	free_dev(h->sums); h->sums = nullptr;
 	free_dev(h->moved); h->moved = nullptr;
 	free_dev(h->counts_dev); h->counts_dev = nullptr;
+	free_dev(h->k1_sums); h->k1_sums = nullptr; h->k1_cap = 0; h->k1_valid = 0;
 	h->means_b_cap = h->means_w_cap = h->means_sq_cap = h->sums_cap = h->moved_cap = h->counts_cap = 0;
 	if (h->h_moved) cudaFreeHost(h->h_moved);
 	if (h->h_counts) cudaFreeHost(h->h_counts);
@@ -277,6 +278,7 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 	h->K = 0;                                    // the resident cluster ids belong to the previous rows
 	QVZ_CUDA(h, cudaStreamSynchronize(h->aux_stream));
 	h->draws_state = 0;                          // ... and so do prefetched draws
+	h->k1_valid = 0;
 
 	qvz_layout &L = h->L;
 	L.n_lines = n_lines;
@@ -334,7 +336,9 @@ extern "C" int qvz_gpu_kmeans_begin(qvz_gpu *h, uint32_t K, const uint8_t *init_
 	if (!rc) rc = ensure_buf(h, &h->means_sq, &h->means_sq_cap, K * sizeof(uint32_t));
 	if (!rc) rc = ensure_buf(h, &h->sums, &h->sums_cap, ((size_t) K * C + K) * sizeof(int64_t));
 	if (!rc) rc = ensure_buf(h, &h->moved, &h->moved_cap, K * sizeof(double));
+	if (!rc && K == 1) rc = ensure_buf(h, &h->k1_sums, &h->k1_cap, ((size_t) C + 1) * sizeof(int64_t));
 	if (rc) return rc;
+	h->k1_valid = 0;                             // a new run reads the rows again
 	if (!h->h_moved) QVZ_CUDA(h, cudaMallocHost(&h->h_moved, QVZ_MAX_K * sizeof(double)));
 	if (!h->h_counts) QVZ_CUDA(h, cudaMallocHost(&h->h_counts, QVZ_MAX_K * sizeof(int64_t)));
 	QVZ_CUDA(h, cudaMemcpyAsync(h->means_b, init_means, (size_t) K * C, cudaMemcpyHostToDevice, h->stream));

@@ -346,10 +346,20 @@ int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev) {
 	const unsigned grid = (unsigned) (blocks < cap ? blocks : cap);
 	QVZ_CUDA(h, cudaMemsetAsync(sums_dev, 0, ((size_t) K * h->L.C + K) * sizeof(int64_t), h->stream));
 	if (K == 1) {
+		// With one cluster the assignment cannot change, so every iteration of this k-means run has the same
+		// column sums as the first one (the reference recomputes them; recalculate_means then finds moved == 0
+		// and stops, src/cluster.c:231-233).  The rows are read once per run; later iterations copy the sums.
+		const size_t bytes = ((size_t) h->L.C + 1) * sizeof(int64_t);
+		if (h->k1_valid) {
+			QVZ_CUDA(h, cudaMemcpyAsync(sums_dev, h->k1_sums, bytes, cudaMemcpyDeviceToDevice, h->stream));
+			return QVZ_OK;
+		}
 		dim3 g((unsigned) ((h->L.P + KS_CHUNK - 1) / KS_CHUNK), C4);
 		qvz_kmeans_single_kernel<<<g, KS_THREADS, 0, h->stream>>>(h->L, h->Xw, h->cl, (unsigned long long *) sums_dev);
 		QVZ_LAUNCHED(h);
 		QVZ_CUDA(h, cudaGetLastError());
+		QVZ_CUDA(h, cudaMemcpyAsync(h->k1_sums, sums_dev, bytes, cudaMemcpyDeviceToDevice, h->stream));
+		h->k1_valid = 1;
 		return QVZ_OK;
 	}
 	switch (K) {
