@@ -358,7 +358,7 @@ extern "C" int qvz_gpu_kmeans_update_dev(qvz_gpu *h, const int64_t *sums_dev, do
 	const uint32_t K = h->km_K, C = h->L.C;
 	int rc = qvz_kmeans_launch_update(h, sums_dev);
 	if (rc) return rc;
-	int64_t *cnt = (int64_t *) h->h_counts;
+	int64_t *cnt = h->h_counts;
 	QVZ_CUDA(h, cudaMemcpyAsync(h->h_moved, h->moved, K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
 	QVZ_CUDA(h, cudaMemcpyAsync(cnt, sums_dev + (size_t) K * C, K * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
 	int empty = 0;

@@ -67,7 +67,7 @@ struct qvz_gpu {
 	int k1_valid;
 	double *moved;           // [K] device
 	double *h_moved;         // pinned [QVZ_MAX_K]
-	uint32_t *h_counts;      // pinned [QVZ_MAX_K] int64 line counts
+	int64_t *h_counts;       // pinned [QVZ_MAX_K] line counts
 	uint32_t *counts_dev;    // conditional-count table of the host-pointer entry point
 	size_t means_b_cap, means_w_cap, means_sq_cap, sums_cap, moved_cap, counts_cap;
 
