@@ -7,7 +7,7 @@
 
 #include "qvz_internal.cuh"
 
-#define QVZ_TARGET_RUNS (148u * 512u)      // runs per shard: enough threads for the draw generator, few enough that the
+#define QVZ_TARGET_RUNS (148u * 768u)      // runs per shard (3 draw-generator CTAs per SM): enough threads for the draw generator, few enough that the
                                            // WELL jump-ahead (one F2 mat-vec per run) stays cheap
 
 enum { EV_A = 0, EV_B, EV_C, EV_D, EV_E, EV_F };

@@ -32,6 +32,8 @@
 // double additions is the same exact integer); DMODE 1 = function of |x-y| (-d L): doubles from shared
 // memory added in column order (bit-identical to the reference's sequence of additions);
 // DMODE 0 = arbitrary 72x72 matrix (-D file) read from global memory.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "qvz_internal.cuh"
@@ -387,6 +389,85 @@ qvz_draws_kernel(qvz_layout L, const uint32_t *__restrict__ run_states, uint32_t
 	}
 }
 
+// The same generator without the FIFO, for lines of at least one full word (C >= 4): every word is consumed in the
+// unrolled step that produced it.  All bookkeeping (full words left in the line, carried draws, line index) is
+// uniform across the grid -- every thread is at the same offset of its own run -- so the branches cost no divergence.
+struct dr_state {
+	uint32_t *dp;        // Dw word of the current line that is written next (per thread)
+	uint32_t ch;         // last WELL word (expanded): its top nb bytes are draws not yet consumed (per thread)
+	uint32_t nb, sh;     // carried draws and the funnel shift 32 - 8*nb of the current line (uniform)
+	uint32_t wleft;      // full words left in the current line; 0 = the line waits for its partial last word (uniform)
+	uint32_t i;          // current line of the run (uniform)
+};
+
+// everything that happens once per line (last full word, partial word, line change): out of line on purpose, so that the
+// 32-step unrolled turn stays small enough for the instruction cache
+__device__ __noinline__ dr_state draws_line_end(dr_state d, uint32_t w, uint32_t *Dw, uint64_t r, uint32_t T, uint64_t P,
+                                                 uint32_t full, uint32_t rem, uint32_t rmask) {
+	bool advance = false;
+	if (d.wleft) {                                   // the last full word of the line
+		st_stream_u32(d.dp, __funnelshift_rc(d.ch, w, d.sh));
+		d.ch = w;
+		d.dp += P;
+		d.wleft = 0;
+		if (rem == 0) advance = true;
+		else if (d.nb >= rem) {                      // its partial word is already in the carry
+			st_stream_u32(d.dp, (d.ch >> d.sh) & rmask);
+			d.nb -= rem;
+			advance = true;
+		}
+	} else {                                         // the partial last word needed this new word
+		st_stream_u32(d.dp, __funnelshift_rc(d.ch, w, d.sh) & rmask);
+		d.ch = w;
+		d.nb += 4 - rem;
+		advance = true;
+	}
+	if (advance) {
+		d.i += 1;
+		d.dp = Dw + (uint64_t) d.i * T + r;
+		d.wleft = full;
+		d.sh = 32 - 8 * d.nb;
+	}
+	return d;
+}
+
+template <int T>
+__device__ __forceinline__ void well_turn_direct(uint32_t (&s)[32], dr_state &d, const qvz_layout &L, uint32_t *Dw, uint64_t r,
+                                                 uint32_t full, uint32_t rem, uint32_t rmask) {
+	if constexpr (T < 32) {
+		const uint32_t w = well_expand_draws(well_step_reg<T>(s));
+		if (d.i < L.Lr) {                                // words past the end of the run (last turn only) are dropped
+			if (d.wleft > 1) {                           // the common case: a full word that is not the line's last
+				st_stream_u32(d.dp, __funnelshift_rc(d.ch, w, d.sh));
+				d.ch = w;
+				d.dp += L.P;
+				d.wleft -= 1;
+			} else d = draws_line_end(d, w, Dw, r, L.T, L.P, full, rem, rmask);
+		}
+		well_turn_direct<T + 1>(s, d, L, Dw, r, full, rem, rmask);
+	}
+}
+
+__global__ void __launch_bounds__(QZ_THREADS)
+qvz_draws_direct_kernel(qvz_layout L, const uint32_t *__restrict__ run_states, uint32_t *__restrict__ Dw)
+{
+	const uint64_t r = (uint64_t) blockIdx.x * QZ_THREADS + threadIdx.x;
+	uint32_t s[32];
+#pragma unroll
+	for (int k = 0; k < 32; ++k) s[k] = run_states[r * 32 + k];
+	const uint32_t C = L.C, full = C >> 2, rem = C & 3;
+	const uint32_t rmask = (1u << (8 * rem)) - 1u;
+	dr_state d;
+	d.dp = Dw + r;
+	d.ch = 0;
+	d.nb = 0;
+	d.sh = 32;
+	d.wleft = full;
+	d.i = 0;
+	const uint32_t turns = (uint32_t) (((uint64_t) L.Lr * C / 4 + 31) / 32);     // Lr % 16 == 0: whole words
+	for (uint32_t t = 0; t < turns; ++t) well_turn_direct<0>(s, d, L, Dw, r, full, rem, rmask);
+}
+
 // largest quantized value any present context can emit for a data value <= smax  -> flags[4]
 __global__ void __launch_bounds__(256)
 qvz_quantize_vmax_kernel(uint64_t entries, const uint32_t *__restrict__ W, const uint8_t *__restrict__ R,
@@ -635,7 +716,10 @@ uint32_t qvz_quantize_batched_group(uint32_t K, uint32_t A) {
 }
 
 int qvz_quantize_draws(qvz_gpu *h) {
-	qvz_draws_kernel<<<h->L.T / QZ_THREADS, QZ_THREADS, 0, h->stream>>>(h->L, h->run_states, h->Dw);
+	if (h->L.C >= 4 && !getenv("QVZ_DRAWS_FIFO"))
+		qvz_draws_direct_kernel<<<h->L.T / QZ_THREADS, QZ_THREADS, 0, h->stream>>>(h->L, h->run_states, h->Dw);
+	else                                             // lines shorter than a WELL word: the general byte-server replay
+		qvz_draws_kernel<<<h->L.T / QZ_THREADS, QZ_THREADS, 0, h->stream>>>(h->L, h->run_states, h->Dw);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;
