@@ -336,7 +336,7 @@ extern "C" int qvz_gpu_kmeans_begin(qvz_gpu *h, uint32_t K, const uint8_t *init_
 	if (!rc) rc = ensure_buf(h, &h->means_sq, &h->means_sq_cap, K * sizeof(uint32_t));
 	if (!rc) rc = ensure_buf(h, &h->sums, &h->sums_cap, ((size_t) K * C + K) * sizeof(int64_t));
 	if (!rc) rc = ensure_buf(h, &h->moved, &h->moved_cap, K * sizeof(double));
-	if (!rc && K == 1) rc = ensure_buf(h, &h->k1_sums, &h->k1_cap, ((size_t) C + 1) * sizeof(int64_t));
+	if (!rc) rc = ensure_buf(h, &h->k1_sums, &h->k1_cap, ((size_t) K * C + K) * sizeof(int64_t));   // the run's local running sums
 	if (rc) return rc;
 	h->k1_valid = 0;                             // a new run reads the rows again
 	if (!h->h_moved) QVZ_CUDA(h, cudaMallocHost(&h->h_moved, QVZ_MAX_K * sizeof(double)));

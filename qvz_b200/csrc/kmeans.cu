@@ -34,7 +34,10 @@
 //            (A warp-REDUX formulation over sorted rows was measured 2x slower: REDUX.SUM is a slow path.)
 __device__ __forceinline__ uint32_t km_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
-template <int KT>
+// INCR = a later iteration of a run: sums[] already holds the column sums of the previous assignment, so only the rows
+// whose cluster CHANGED move their bytes (+ new cluster, - old cluster, signed 32-bit partials): no sort, no scatter, no
+// second tile.  Integer sums: the totals are exactly those of a full recount.
+template <int KT, bool INCR>
 __global__ void __launch_bounds__(QVZ_THREADS)
 qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t *__restrict__ cl,
                          const uint32_t *__restrict__ means_w, const uint32_t *__restrict__ means_sq,
@@ -49,7 +52,7 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
 	uint64_t *bar = (uint64_t *) sm;
 	uint32_t *tile = sm + 4;                             // [C4][pitch]   (TMA destination: 16-byte aligned rows)
 	uint32_t *stile = tile + C4 * pitch;                 // [C4][spitch]  rows sorted by cluster
-	uint32_t *mean4 = stile + ((C4 * spitch + 3) & ~3u); // [C4][KP]
+	uint32_t *mean4 = INCR ? stile : stile + ((C4 * spitch + 3) & ~3u);   // [C4][KP]   (INCR has no sorted tile)
 	uint32_t *acc = mean4 + C4 * KP;                     // [K][C4*4]
 	uint32_t *msq = acc + K * C4 * 4;                    // [KP]
 	uint32_t *cnt = msq + KP;                            // [K]
@@ -98,7 +101,8 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
 			    "}" ::"r"(addr), "r"(parity) : "memory");
 		}
 		const uint64_t p = t * R + tid;
-		const bool valid = cl[p] != QVZ_NO_LINE;
+		const uint32_t old = cl[p];
+		const bool valid = old != QVZ_NO_LINE;
 		uint32_t best = 0;
 		{
 			uint32_t D[KP];
@@ -131,6 +135,36 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
 					}
 				}
 			}
+		}
+		if (INCR) {
+			const bool changed = valid && best != old;
+			if (changed) cl[p] = (uint8_t) best;
+			uint32_t mask = __ballot_sync(0xFFFFFFFFu, changed);
+			while (mask) {                               // one changed row at a time, the warp's lanes over its column words
+				const uint32_t src = __ffs(mask) - 1;
+				mask &= mask - 1;
+				const uint32_t nk = __shfl_sync(0xFFFFFFFFu, best, src), ok = __shfl_sync(0xFFFFFFFFu, old, src);
+				const uint32_t *tr = tile + (warp * 32 + src);
+				for (uint32_t c4 = lane; c4 < C4; c4 += 32) {
+					const uint32_t w = tr[c4 * pitch];
+					uint32_t *an = acc + (nk * C4 + c4) * 4, *ao = acc + (ok * C4 + c4) * 4;
+#pragma unroll
+					for (uint32_t j = 0; j < 4; ++j) {
+						const uint32_t b = (w >> (8 * j)) & 0xFFu;
+						if (b) {
+							atomicAdd(an + j, b);
+							atomicSub(ao + j, b);
+						}
+					}
+				}
+				if (lane == 0) {
+					atomicAdd(&cnt[nk], 1u);
+					atomicSub(&cnt[ok], 1u);
+				}
+			}
+			__syncthreads();                             // the tile has been consumed
+			if (t + gridDim.x < tiles) fetch(t + gridDim.x);
+			continue;
 		}
 		if (valid) cl[p] = (uint8_t) best;
 		const uint32_t key = valid ? best : 0;           // empty slots hold zero words: harmless in any list
@@ -204,11 +238,12 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
 		}
 		__syncthreads();                                 // stile and off are reused by the next tile
 	}
-	for (uint32_t i = tid; i < K * C4 * 4; i += R) {
+	__syncthreads();
+	for (uint32_t i = tid; i < K * C4 * 4; i += R) {     // INCR partials are signed: sign-extend (two's complement add)
 		const uint32_t k = i / (C4 * 4), c = i - k * C4 * 4;
-		if (c < L.C && acc[i]) atomicAdd(&sums[(uint64_t) k * L.C + c], (unsigned long long) acc[i]);
+		if (c < L.C && acc[i]) atomicAdd(&sums[(uint64_t) k * L.C + c], INCR ? (unsigned long long) (long long) (int) acc[i] : (unsigned long long) acc[i]);
 	}
-	if (tid < K && cnt[tid]) atomicAdd(&sums[(uint64_t) K * L.C + tid], (unsigned long long) cnt[tid]);
+	if (tid < K && cnt[tid]) atomicAdd(&sums[(uint64_t) K * L.C + tid], INCR ? (unsigned long long) (long long) (int) cnt[tid] : (unsigned long long) cnt[tid]);
 }
 
 // K == 1: assign_cluster has nothing to compare -- every line lands in cluster 0 -- so one iteration is just
@@ -318,63 +353,75 @@ qvz_kmeans_update_kernel(uint32_t K, uint32_t C, uint32_t C4, const unsigned lon
 	}
 }
 
-static size_t assign_smem(uint32_t K, uint32_t C4, uint32_t R) {
+static size_t assign_smem(uint32_t K, uint32_t C4, uint32_t R, bool incr = false) {
 	const uint32_t NW = R / 32, KP = ((K <= 8 ? K : QVZ_MAX_K) + 3) & ~3u;
-	size_t words = 4 + (size_t) C4 * (R + 4) + (((size_t) C4 * (R + 1) + 3) & ~(size_t) 3) + (size_t) C4 * KP + (size_t) K * C4 * 4 + KP + K + (NW + 2) * K;
+	size_t words = 4 + (size_t) C4 * (R + 4) + (incr ? 0 : (((size_t) C4 * (R + 1) + 3) & ~(size_t) 3)) + (size_t) C4 * KP + (size_t) K * C4 * 4 + KP + K + (NW + 2) * K;
 	words += 4;
 	return words * sizeof(uint32_t);
 }
 
 template <int KT>
-static void launch_assign(qvz_gpu *h, int64_t *sums_dev, unsigned grid, unsigned R, size_t smem) {
-	auto kern = qvz_kmeans_assign_kernel<KT>;
-	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-	kern<<<grid, R, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K,
-	                                   (unsigned long long *) sums_dev);
+static void launch_assign(qvz_gpu *h, int64_t *sums_dev, unsigned grid, unsigned R, size_t smem, bool incr) {
+	if (incr) {
+		auto kern = qvz_kmeans_assign_kernel<KT, true>;
+		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		kern<<<grid, R, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K, (unsigned long long *) sums_dev);
+	} else {
+		auto kern = qvz_kmeans_assign_kernel<KT, false>;
+		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		kern<<<grid, R, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K, (unsigned long long *) sums_dev);
+	}
 }
 
 int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev) {
 	const uint32_t K = h->km_K, C4 = h->L.C4;
+	const size_t sum_bytes = ((size_t) K * h->L.C + K) * sizeof(int64_t);
+	if (K == 1) {
+		// With one cluster the assignment cannot change, so every iteration of this k-means run has the same
+		// column sums as the first one (the reference recomputes them; recalculate_means then finds moved == 0
+		// and stops, src/cluster.c:231-233).  The rows are read once per run; later iterations copy the sums.
+		if (h->k1_valid) {
+			QVZ_CUDA(h, cudaMemcpyAsync(sums_dev, h->k1_sums, sum_bytes, cudaMemcpyDeviceToDevice, h->stream));
+			return QVZ_OK;
+		}
+		QVZ_CUDA(h, cudaMemsetAsync(sums_dev, 0, sum_bytes, h->stream));
+		dim3 g((unsigned) ((h->L.P + KS_CHUNK - 1) / KS_CHUNK), C4);
+		qvz_kmeans_single_kernel<<<g, KS_THREADS, 0, h->stream>>>(h->L, h->Xw, h->cl, (unsigned long long *) sums_dev);
+		QVZ_LAUNCHED(h);
+		QVZ_CUDA(h, cudaGetLastError());
+		QVZ_CUDA(h, cudaMemcpyAsync(h->k1_sums, sums_dev, sum_bytes, cudaMemcpyDeviceToDevice, h->stream));
+		h->k1_valid = 1;
+		return QVZ_OK;
+	}
+	// K >= 2: the first iteration of a run counts everything; later ones only move the rows that changed cluster.
+	// k1_sums doubles as the run's local running sums (the caller may all-reduce sums_dev in place).
+	const bool incr = h->k1_valid && !getenv("QVZ_KM_FULL");
 	unsigned R = 128;                                                   // measured: 128-row tiles (3-5 CTAs per SM) beat 256 and 64
 	while (R > 64 && assign_smem(K, C4, R) > 110 * 1024) R >>= 1;       // keep >= 2 CTAs per SM when possible
 	if (const char *e = getenv("QVZ_KM_R")) R = (unsigned) atoi(e);     // tuning knob: 64, 128 or 256
-	const size_t smem = assign_smem(K, C4, R);
+	const size_t smem = assign_smem(K, C4, R, incr);
 	if (smem > 220 * 1024) QVZ_FAIL(h, QVZ_ERR_UNSUPPORTED, "k-means: K*columns too large for shared memory");
 	const uint64_t blocks = h->L.P / R;
 	const uint64_t per_sm = (220 * 1024) / smem < (2048 / R) ? (220 * 1024) / smem : (2048 / R);
 	const uint64_t cap = (uint64_t) h->sm_count * (per_sm ? per_sm : 1);
 	const unsigned grid = (unsigned) (blocks < cap ? blocks : cap);
-	QVZ_CUDA(h, cudaMemsetAsync(sums_dev, 0, ((size_t) K * h->L.C + K) * sizeof(int64_t), h->stream));
-	if (K == 1) {
-		// With one cluster the assignment cannot change, so every iteration of this k-means run has the same
-		// column sums as the first one (the reference recomputes them; recalculate_means then finds moved == 0
-		// and stops, src/cluster.c:231-233).  The rows are read once per run; later iterations copy the sums.
-		const size_t bytes = ((size_t) h->L.C + 1) * sizeof(int64_t);
-		if (h->k1_valid) {
-			QVZ_CUDA(h, cudaMemcpyAsync(sums_dev, h->k1_sums, bytes, cudaMemcpyDeviceToDevice, h->stream));
-			return QVZ_OK;
-		}
-		dim3 g((unsigned) ((h->L.P + KS_CHUNK - 1) / KS_CHUNK), C4);
-		qvz_kmeans_single_kernel<<<g, KS_THREADS, 0, h->stream>>>(h->L, h->Xw, h->cl, (unsigned long long *) sums_dev);
-		QVZ_LAUNCHED(h);
-		QVZ_CUDA(h, cudaGetLastError());
-		QVZ_CUDA(h, cudaMemcpyAsync(h->k1_sums, sums_dev, bytes, cudaMemcpyDeviceToDevice, h->stream));
-		h->k1_valid = 1;
-		return QVZ_OK;
-	}
+	int64_t *target = incr ? h->k1_sums : sums_dev;                     // INCR adds signed deltas to the running sums
+	if (!incr) QVZ_CUDA(h, cudaMemsetAsync(sums_dev, 0, sum_bytes, h->stream));
 	switch (K) {
-	case 1: launch_assign<1>(h, sums_dev, grid, R, smem); break;
-	case 2: launch_assign<2>(h, sums_dev, grid, R, smem); break;
-	case 3: launch_assign<3>(h, sums_dev, grid, R, smem); break;
-	case 4: launch_assign<4>(h, sums_dev, grid, R, smem); break;
-	case 5: launch_assign<5>(h, sums_dev, grid, R, smem); break;
-	case 6: launch_assign<6>(h, sums_dev, grid, R, smem); break;
-	case 7: launch_assign<7>(h, sums_dev, grid, R, smem); break;
-	case 8: launch_assign<8>(h, sums_dev, grid, R, smem); break;
-	default: launch_assign<0>(h, sums_dev, grid, R, smem); break;
+	case 2: launch_assign<2>(h, target, grid, R, smem, incr); break;
+	case 3: launch_assign<3>(h, target, grid, R, smem, incr); break;
+	case 4: launch_assign<4>(h, target, grid, R, smem, incr); break;
+	case 5: launch_assign<5>(h, target, grid, R, smem, incr); break;
+	case 6: launch_assign<6>(h, target, grid, R, smem, incr); break;
+	case 7: launch_assign<7>(h, target, grid, R, smem, incr); break;
+	case 8: launch_assign<8>(h, target, grid, R, smem, incr); break;
+	default: launch_assign<0>(h, target, grid, R, smem, incr); break;
 	}
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
+	if (incr) QVZ_CUDA(h, cudaMemcpyAsync(sums_dev, h->k1_sums, sum_bytes, cudaMemcpyDeviceToDevice, h->stream));
+	else QVZ_CUDA(h, cudaMemcpyAsync(h->k1_sums, sums_dev, sum_bytes, cudaMemcpyDeviceToDevice, h->stream));
+	h->k1_valid = 1;
 	return QVZ_OK;
 }
 

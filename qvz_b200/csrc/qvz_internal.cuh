@@ -62,7 +62,7 @@ struct qvz_gpu {
 	uint32_t *means_w;       // [K][C4] same, packed for dp4a (zero padded)
 	uint32_t *means_sq;      // [K] sum of squares of each centroid
 	int64_t *sums;           // [K*C + K] column sums, then line counts
-	int64_t *k1_sums;        // K == 1: the sums of the first iteration of the current run (see kmeans.cu)
+	int64_t *k1_sums;        // this shard's running sums of the current k-means run (kmeans.cu): K == 1 reuses them, K >= 2 updates them
 	size_t k1_cap;
 	int k1_valid;
 	double *moved;           // [K] device
