@@ -14,12 +14,11 @@
 // same address (measured on B200: 1 cycle per warp instruction when the distinct addresses fall in distinct
 // banks, ~3.6 for random addresses; tools/ubench/atoms.cu).  Neighbouring reads agree on (prev, cur) very
 // often, so all lanes count the same column at the same step (few distinct addresses per instruction).
-// WIDE = 32-bit counters (K <= 2: no two bins share a word, so merging works on whole bins); otherwise
-// packed 16-bit pairs (5 clusters per pass; a chunk is < 65 536 slots so no counter can overflow).
+// The slices are A x A 32-bit counters, A-1 = the largest symbol present in the rows (found at ingest): for
+// Phred+33 data with Q <= 41 a slice is 7 KB instead of 20 KB, so up to 7 clusters are counted in one pass.
 #include "qvz_internal.cuh"
 
 #define CC_THREADS 1024
-#define CC_BINS (72u * 72u)
 #define CC_PAD 8u                               // words between slices
 
 __device__ __forceinline__ uint4 cc_ldg128(const uint32_t *p) {
@@ -34,12 +33,13 @@ __device__ __forceinline__ void cc_red_shared(uint32_t addr, uint32_t v) {
 // A thread takes 4 consecutive slots per iteration (16-byte loads of the word column, of the previous word
 // column and one 4-byte load of the cluster ids): 16 symbols per 3 loads.  TAIL = this word column holds
 // the last, partial word of the lines (columns past C must not be counted).
-template <bool WIDE, bool TAIL>
+template <bool TAIL>
 __device__ __forceinline__ void cc_count_chunk(const uint32_t *__restrict__ xc, const uint32_t *__restrict__ xp,
                                                const uint8_t *__restrict__ clp, uint32_t n, bool first, bool single,
-                                               uint32_t kbase, uint32_t G, uint32_t tab_addr, uint32_t live)
+                                               uint32_t kbase, uint32_t G, uint32_t tab_addr, uint32_t live,
+                                               uint32_t A, uint32_t slice_bytes)
 {
-	constexpr uint32_t SLICE = (WIDE ? CC_BINS : CC_BINS / 2) + CC_PAD;
+	const uint32_t row_bytes = A * 4;
 	for (uint32_t i = 4 * threadIdx.x; i < n; i += 4 * CC_THREADS) {
 		const uint4 w4 = cc_ldg128(xc + i);
 		const uint4 q4 = first ? make_uint4(0x21212121u, 0x21212121u, 0x21212121u, 0x21212121u) : cc_ldg128(xp + i);
@@ -51,39 +51,32 @@ __device__ __forceinline__ void cc_count_chunk(const uint32_t *__restrict__ xc, 
 			if (ws[u] != 0u && g < G) {                  // a slot without a line holds zero words (real bytes are >= 33)
 				const uint32_t w = ws[u] - 0x21212121u;  // ingest guarantees every real byte >= 33: no borrow
 				const uint32_t pv = __funnelshift_r(qs[u] - 0x21212121u, w, 24);   // bytes: prev of byte 0, 1, 2, 3
-				const uint32_t wr = w, pr = pv;
-				const uint32_t gb = single ? 0u : g * (4 * SLICE * 4);
-				// bins of bytes (0, 2) and (1, 3) as 16-bit pairs: prev*72 + cur <= 5183, times 4 still fits 16 bits
-				const uint32_t be = (pr & 0x00FF00FFu) * (WIDE ? 288u : 72u) + ((wr & 0x00FF00FFu) << (WIDE ? 2 : 0));
-				const uint32_t bo = ((pr >> 8) & 0x00FF00FFu) * (WIDE ? 288u : 72u) + (((wr >> 8) & 0x00FF00FFu) << (WIDE ? 2 : 0));
+				const uint32_t gb = single ? 0u : g * (4 * slice_bytes);
+				// counter byte offsets of bytes (0, 2) and (1, 3) as 16-bit pairs: (prev*A + cur)*4 <= 71*288 + 284 < 2^16
+				const uint32_t be = (pv & 0x00FF00FFu) * row_bytes + ((w & 0x00FF00FFu) << 2);
+				const uint32_t bo = ((pv >> 8) & 0x00FF00FFu) * row_bytes + (((w >> 8) & 0x00FF00FFu) << 2);
 #pragma unroll
 				for (uint32_t j = 0; j < 4; ++j) {
 					const uint32_t pair = (j & 1) ? bo : be;
-					const uint32_t bin = (j & 2) ? pair >> 16 : pair & 0xFFFFu;      // WIDE: byte offset of the counter
-					if (WIDE) {
-						if (!TAIL || j < live) cc_red_shared(tab_addr + j * SLICE * 4 + gb + bin, 1u);
-					} else {
-						const uint32_t a = tab_addr + j * SLICE * 4 + gb + ((bin << 1) & ~3u);
-						if (!TAIL || j < live) cc_red_shared(a, 1u << (16 * (bin & 1)));
-					}
+					const uint32_t off = (j & 2) ? pair >> 16 : pair & 0xFFFFu;
+					if (!TAIL || j < live) cc_red_shared(tab_addr + j * slice_bytes + gb + off, 1u);
 				}
 			}
 		}
 	}
 }
 
-template <bool WIDE>
 __global__ void __launch_bounds__(CC_THREADS, 1)
 qvz_cond_counts_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint8_t *__restrict__ cl,
-                       uint32_t K, uint32_t G, uint32_t chunk, uint32_t *__restrict__ counts)
+                       uint32_t K, uint32_t G, uint32_t A, uint32_t chunk, uint32_t *__restrict__ counts)
 {
-	extern __shared__ uint32_t tab[];            // [G][4][SLICE]
-	constexpr uint32_t SLICE = (WIDE ? CC_BINS : CC_BINS / 2) + CC_PAD;
+	extern __shared__ uint32_t tab[];            // [G][4][slice]
+	const uint32_t slice = A * A + CC_PAD;
 	const uint32_t c4 = blockIdx.x;
 	const uint32_t kbase = blockIdx.z * G;
 	const uint64_t p0 = (uint64_t) blockIdx.y * chunk;
 	const uint64_t p1 = (p0 + chunk < L.P) ? p0 + chunk : L.P;      // chunk % 4096 == 0 and P % 4096 == 0
-	const uint32_t words = G * 4 * SLICE;
+	const uint32_t words = G * 4 * slice;
 
 	for (uint32_t i = threadIdx.x; i < words; i += CC_THREADS) tab[i] = 0;
 	__syncthreads();
@@ -93,52 +86,41 @@ qvz_cond_counts_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint
 	const uint32_t *xc = Xw + (uint64_t) c4 * L.P + p0;
 	const uint32_t *xp = xc - L.P;               // only dereferenced for c4 > 0
 	const uint32_t n = (uint32_t) (p1 - p0);
-	if (4 * c4 + 3 < L.C) cc_count_chunk<WIDE, false>(xc, xp, cl + p0, n, c4 == 0, K == 1, kbase, G, tab_addr, live);
-	else cc_count_chunk<WIDE, true>(xc, xp, cl + p0, n, c4 == 0, K == 1, kbase, G, tab_addr, live);
+	if (4 * c4 + 3 < L.C) cc_count_chunk<false>(xc, xp, cl + p0, n, c4 == 0, K == 1, kbase, G, tab_addr, live, A, slice * 4);
+	else cc_count_chunk<true>(xc, xp, cl + p0, n, c4 == 0, K == 1, kbase, G, tab_addr, live, A, slice * 4);
 	__syncthreads();
 
 	const uint64_t per_cluster = (uint64_t) (1 + 72 * (L.C - 1)) * 72;
 	for (uint32_t i = threadIdx.x; i < words; i += CC_THREADS) {
 		const uint32_t v = tab[i];
 		if (!v) continue;
-		const uint32_t slice = i / SLICE, wbin = i - slice * SLICE;
-		const uint32_t g = slice >> 2, j = slice & 3, col = 4 * c4 + j;
-		if (kbase + g >= K || wbin >= SLICE - CC_PAD) continue;
-		// column 0 only ever sees prev == 0 => bins 0..71 => pmfs[0]; column c >= 1 starts at pmfs[1 + (c-1)*72]
-		uint32_t *dst = counts + (uint64_t) (kbase + g) * per_cluster + (col ? (uint64_t) (1 + (col - 1) * 72) * 72 : 0);
-		if (WIDE) {
-			atomicAdd(dst + wbin, v);
-		} else {
-			if (v & 0xFFFFu) atomicAdd(dst + 2 * wbin, v & 0xFFFFu);
-			if (v >> 16) atomicAdd(dst + 2 * wbin + 1, v >> 16);
-		}
+		const uint32_t s = i / slice, cell = i - s * slice;
+		const uint32_t g = s >> 2, j = s & 3, col = 4 * c4 + j;
+		if (kbase + g >= K || cell >= A * A) continue;
+		const uint32_t prev = cell / A, cur = cell - prev * A;
+		// column 0 only ever sees prev == 0 => pmfs[0]; column c >= 1, previous value prev => pmfs[1 + (c-1)*72 + prev]
+		uint32_t *dst = counts + (uint64_t) (kbase + g) * per_cluster + (col ? (uint64_t) (1 + (col - 1) * 72 + prev) * 72 : 0);
+		atomicAdd(dst + cur, v);
 	}
 }
 
 int qvz_cond_counts_launch(qvz_gpu *h, uint32_t *counts_dev) {
 	const uint32_t K = h->K;
-	const bool wide = K <= 2;
-	const uint32_t G = wide ? K : (K < 5 ? K : 5);
-	const size_t smem = (size_t) G * 4 * ((wide ? CC_BINS : CC_BINS / 2) + CC_PAD) * sizeof(uint32_t);
-	// chunk: a multiple of the per-iteration stride; packed counters need < 65 536 slots per CTA; wide ones are
-	// sized for ~16 CTAs per SM over the whole grid so that zeroing/flushing the slices stays negligible
-	uint32_t chunk = 61440;
-	if (wide) {
-		const uint64_t want = (uint64_t) h->sm_count * 16 / h->L.C4 + 1;
-		uint64_t c = (h->L.P + want - 1) / want;
-		c = (c + 4095) / 4096 * 4096;
-		chunk = (uint32_t) (c < 61440 ? 61440 : c);
-	}
+	const uint32_t A = h->smax + 1 > 72 ? 72 : h->smax + 1;
+	const size_t slice_bytes = ((size_t) A * A + CC_PAD) * sizeof(uint32_t);
+	uint32_t G = (uint32_t) ((200 * 1024) / (4 * slice_bytes));       // clusters per pass that fit shared memory (2 at A = 72, 7 at A = 42)
+	if (G > K) G = K;
+	const size_t smem = (size_t) G * 4 * slice_bytes;
+	// chunk of slots per CTA: sized for ~16 CTAs per SM over the whole grid so that zeroing/flushing the slices stays negligible
+	const uint64_t want = (uint64_t) h->sm_count * 16 / h->L.C4 + 1;
+	uint64_t c = (h->L.P + want - 1) / want;
+	c = (c + 4095) / 4096 * 4096;
+	const uint32_t chunk = (uint32_t) (c < 61440 ? 61440 : c);
 	QVZ_CUDA(h, cudaMemsetAsync(counts_dev, 0, qvz_gpu_cond_counts_len(K, h->L.C) * sizeof(uint32_t), h->stream));
 	dim3 grid(h->L.C4, (unsigned) ((h->L.P + chunk - 1) / chunk), (K + G - 1) / G);
 	// the last cluster group may be partial: out-of-range ids are skipped by g >= G / kbase + g >= K
-	if (wide) {
-		QVZ_CUDA(h, cudaFuncSetAttribute(qvz_cond_counts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		qvz_cond_counts_kernel<true><<<grid, CC_THREADS, smem, h->stream>>>(h->L, h->Xw, h->cl, K, G, chunk, counts_dev);
-	} else {
-		QVZ_CUDA(h, cudaFuncSetAttribute(qvz_cond_counts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		qvz_cond_counts_kernel<false><<<grid, CC_THREADS, smem, h->stream>>>(h->L, h->Xw, h->cl, K, G, chunk, counts_dev);
-	}
+	QVZ_CUDA(h, cudaFuncSetAttribute(qvz_cond_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	qvz_cond_counts_kernel<<<grid, CC_THREADS, smem, h->stream>>>(h->L, h->Xw, h->cl, K, G, A, chunk, counts_dev);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;
