@@ -47,7 +47,8 @@ def test_cli_reproduces_golden_file(tmp_path, name):
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/qvz_ref_det not built")
-@pytest.mark.parametrize("n,c,flags,gpus", [(30_000, 36, ["-f", "0.5", "-d", "A", "-c", "3", "-T", "4"], 1),
+@pytest.mark.parametrize("n,c,flags,gpus", [(60_000, 150, ["-f", "0.5", "-d", "A", "-c", "3", "-T", "4"], 1),   # cfg3's command line and read length
+                                            (30_000, 36, ["-f", "0.5", "-d", "A", "-c", "3", "-T", "4"], 1),
                                             (20_000, 50, ["-r", "2", "-d", "L", "-c", "1"], 1),
                                             (25_000, 30, ["-f", "1.0", "-d", "M", "-c", "2"], 2)])
 def test_cli_vs_reference_binary(tmp_path, n, c, flags, gpus):
