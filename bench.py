@@ -418,7 +418,10 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": f"{cfg['name']}: {cfg['lines']} lines x {c} columns, {k} cluster(s)", "lines_per_gpu": cfg["lines"], "columns": c, "clusters": k},
+           "config": {"workload": f"{cfg['name']}: {cfg['lines']} lines x {c} columns per GPU, {k} cluster(s), "
+                                  f"{'-f' if cfg['mode']=='ratio' else '-r'} {cfg['ratio']} -d {cfg['dist']}",
+                      "lines_per_gpu": cfg["lines"], "columns": c, "clusters": k,
+                      "tables": "the reference's own generate_codebooks on the sample", "sharding": "single host thread"},
            "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
            "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
