@@ -309,7 +309,12 @@ int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int dmode) {
 //   becomes NaN (double modes) or >= 2^31 (integer mode) and is reported once per line instead of being
 //   checked per symbol.
 // =====================================================================================================
-#define QB_THREADS 1024
+#ifndef QB_THREADS
+#define QB_THREADS 1024                 // threads per CTA of the walk (tuning: -DQB_THREADS=512 -DQB_CTAS=2)
+#endif
+#ifndef QB_CTAS
+#define QB_CTAS 1                       // resident walk CTAs per SM
+#endif
 #define QB_LPT 4
 #define QB_LINES (QB_THREADS * QB_LPT)
 #define QB_POISON 72u
@@ -556,7 +561,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 
 // S = columns staged per barrier (4, 2 or 1: the largest whose double buffer fits shared memory)
 template <int DMODE, bool WANT_QV, int S>
-__global__ void __launch_bounds__(QB_THREADS, 1)
+__global__ void __launch_bounds__(QB_THREADS, QB_CTAS)
 qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint32_t *__restrict__ Dw,
                             const uint8_t *__restrict__ cl, const uint8_t *__restrict__ G,
                             const uint8_t *__restrict__ R, const double *__restrict__ D, uint32_t K,
@@ -711,7 +716,7 @@ static size_t batched_smem(uint32_t K, uint32_t A, uint32_t S) {
 // columns staged per barrier: the largest of 4, 2, 1 whose double buffer fits; 0 = batched path unusable
 uint32_t qvz_quantize_batched_group(uint32_t K, uint32_t A) {
 	for (uint32_t S = 4; S >= 1; S >>= 1)
-		if (batched_smem(K, A, S) <= 200 * 1024) return S;
+		if (batched_smem(K, A, S) <= (QB_CTAS == 1 ? 200 : 108) * 1024) return S;
 	return 0;
 }
 
@@ -747,7 +752,8 @@ static void launch_batched(qvz_gpu *h, uint32_t K, uint32_t A) {
 	const size_t smem = batched_smem(K, A, S);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	const uint64_t nbatch = h->L.P / QB_LINES;
-	const unsigned grid = (unsigned) (nbatch < (uint64_t) h->sm_count ? nbatch : (uint64_t) h->sm_count);
+	const uint64_t resident = (uint64_t) h->sm_count * QB_CTAS;
+	const unsigned grid = (unsigned) (nbatch < resident ? nbatch : resident);
 	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->G, h->R, h->D, K, A, h->Yw,
 	                                            WANT_QV ? h->Qw : nullptr, h->Ep, h->flags);
 }
