@@ -310,3 +310,48 @@ def test_quantize_custom_distortion_matrix(gpu, oracle):
     o = oracle.quantize(rows, c, ids, t, DEBUG_SEED)
     assert np.array_equal(q["symbols"], o["symbols"]) and np.array_equal(q["qv"], o["qv"])
     assert np.array_equal(q["line_err"], o["line_err"])
+
+
+def test_beyond_4g_symbols(gpu, oracle):
+    """Maximum sizes: one shard with more than 2^32 symbols (29.2M x 150 = 4.38e9; cfg4 on one B200 is 7x that).
+    Every slot, word and draw index past 2^32 must be 64-bit clean.  Checked through properties that do not need a
+    CPU pass over 4 GB: exact column sums, count totals, and the walk of the first and the last lines of the big
+    shard against (a) the same lines loaded as a small shard at the same global offset and (b) the CPU oracle."""
+    import torch
+    from qvz_b200 import lib
+    n, c, k, tail = 29_200_000, 150, 2, 4096
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2**30:
+        pytest.skip("needs 60 GB of free device memory")
+    dev = synth_rows(n, c, seed=99, device="cuda")
+    colsum = sum(dev[lo:lo + 1_000_000, :c].sum(0, dtype=torch.int64) for lo in range(0, n, 1_000_000)).cpu().numpy()
+    rows = dev.cpu().numpy()
+    del dev
+    torch.cuda.empty_cache()
+    assert n * c > 2**32
+    _load(gpu, rows, c)
+    # K = 1: the centroid is the exact integer column mean
+    km1 = gpu.kmeans(rows[[930_886], :c], 4.0, want_ids=False)
+    assert np.array_equal(km1["means"][0], (colsum // n).astype(np.uint8))
+    # K = 2: sizes, and count tables that hold every line once per column
+    km = gpu.kmeans(rows[[930_886, 17_636_915], :c], 4.0)
+    ids = km["ids"]
+    assert km["counts"].astype(np.int64).sum() == n and np.array_equal(np.bincount(ids, minlength=k), km["counts"])
+    counts = gpu.cond_counts()
+    assert np.array_equal(counts.reshape(k, -1).sum(1, dtype=np.uint64), km["counts"].astype(np.uint64) * c)
+    t = synthetic_tables(k, c, seed=9)
+    q = gpu.quantize(t, DEBUG_SEED, want_err=True)
+    small = lib.Handle(0)
+    try:
+        for lo in (0, n - tail):                                     # n - tail is a multiple of 4 (WELL word boundary)
+            part = np.ascontiguousarray(rows[lo:lo + tail])
+            small.load_rows(part, tail, c, c + 1, first_line=lo)
+            small.set_clusters(k, ids[lo:lo + tail])
+            qs = small.quantize(t, DEBUG_SEED, want_err=True)
+            assert np.array_equal(qs["symbols"], q["symbols"][lo:lo + tail]), lo
+            assert np.array_equal(qs["line_err"], q["line_err"][lo:lo + tail]), lo
+            o = oracle.quantize(part, c, ids[lo:lo + tail], t, DEBUG_SEED, first_line=lo)
+            assert np.array_equal(o["symbols"], qs["symbols"]), lo
+            assert np.array_equal(o["line_err"], qs["line_err"]), lo
+    finally:
+        small.close()
