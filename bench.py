@@ -271,15 +271,22 @@ def run_native(args):
     # (1 B per QV read, 1 B per cluster id, 1 B per emitted symbol; the WELL draws are an
     # intermediate, not algorithmic I/O -- the draw generator's time is shown but it has no roofline of its own)
     walk_ms = stage["quantize_ms"] - stage["quantize_draws_ms"]
-    km_launches = 1 if k == 1 else max(iters, 1)   # K = 1: the rows are read once per run, later iterations reuse the sums
-    kern = {"kmeans_assign": (stage["kmeans_assign_ms"] / km_launches, sym_per_rank + n),
-            "cond_counts": (stage["cond_counts_ms"], sym_per_rank + n),
-            "quantize_walk": (walk_ms, 2 * sym_per_rank + n)}
-    share = {"kmeans_assign": stage["kmeans_assign_ms"], "cond_counts": stage["cond_counts_ms"], "quantize_walk": walk_ms}
+    if k == 1:
+        # one cluster: the k-means stage IS the counting pass (its column sums are marginals of the count table, csrc/kmeans.cu);
+        # qvz_gpu_cond_counts then hands out the table that pass left on the device
+        counts_ms = stage["kmeans_assign_ms"] + stage["cond_counts_ms"]
+        kern = {"cond_counts": (counts_ms, sym_per_rank + n), "quantize_walk": (walk_ms, 2 * sym_per_rank + n)}
+        share = {"cond_counts": counts_ms, "quantize_walk": walk_ms}
+    else:
+        km_launches = max(iters, 1)
+        kern = {"kmeans_assign": (stage["kmeans_assign_ms"] / km_launches, sym_per_rank + n),
+                "cond_counts": (stage["cond_counts_ms"], sym_per_rank + n),
+                "quantize_walk": (walk_ms, 2 * sym_per_rank + n)}
+        share = {"kmeans_assign": stage["kmeans_assign_ms"], "cond_counts": stage["cond_counts_ms"], "quantize_walk": walk_ms}
     dom = max(share, key=share.get)                # dominant kernel = largest share of the step
     dur_ms, alg_bytes = kern[dom]
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
-    names = {"kmeans_assign": "qvz_kmeans_single_kernel" if k == 1 else "qvz_kmeans_assign_kernel", "cond_counts": "qvz_cond_counts_kernel",
+    names = {"kmeans_assign": "qvz_kmeans_assign_kernel", "cond_counts": "qvz_cond_counts_kernel",
              "quantize_walk": "qvz_quantize_batched_kernel"}
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": ncu_traffic(dom, cfg),
@@ -321,7 +328,7 @@ def ncu_traffic(kernel, cfg):
         return None
     per = json.load(open(files[-1]))["dram_bytes_per_launch"]
     pick = {"quantize_walk": ("qvz_quantize_batched_kernel",), "cond_counts": ("qvz_cond_counts_kernel",),
-            "kmeans_assign": ("qvz_kmeans_single_kernel", "qvz_kmeans_assign_kernel")}[kernel]
+            "kmeans_assign": ("qvz_kmeans_assign_kernel",)}[kernel]
     tot = sum(v for k, v in per.items() if any(p in k for p in pick))
     return int(tot) if tot else None
 

@@ -151,7 +151,7 @@ static void release_kmeans(qvz_gpu *h) {
 	free_dev(h->means_sq); h->means_sq = nullptr;
 	free_dev(h->sums); h->sums = nullptr;
 	free_dev(h->moved); h->moved = nullptr;
-	free_dev(h->counts_dev); h->counts_dev = nullptr;
+	free_dev(h->counts_dev); h->counts_dev = nullptr; h->counts_cached = 0;
 	free_dev(h->k1_sums); h->k1_sums = nullptr; h->k1_cap = 0; h->k1_valid = 0;
 	h->means_b_cap = h->means_w_cap = h->means_sq_cap = h->sums_cap = h->moved_cap = h->counts_cap = 0;
 	if (h->h_moved) cudaFreeHost(h->h_moved);
@@ -279,6 +279,7 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 	QVZ_CUDA(h, cudaStreamSynchronize(h->aux_stream));
 	h->draws_state = 0;                          // ... and so do prefetched draws
 	h->k1_valid = 0;
+	h->counts_cached = 0;
 
 	qvz_layout &L = h->L;
 	L.n_lines = n_lines;
@@ -337,8 +338,11 @@ extern "C" int qvz_gpu_kmeans_begin(qvz_gpu *h, uint32_t K, const uint8_t *init_
 	if (!rc) rc = ensure_buf(h, &h->sums, &h->sums_cap, ((size_t) K * C + K) * sizeof(int64_t));
 	if (!rc) rc = ensure_buf(h, &h->moved, &h->moved_cap, K * sizeof(double));
 	if (!rc) rc = ensure_buf(h, &h->k1_sums, &h->k1_cap, ((size_t) K * C + K) * sizeof(int64_t));   // the run's local running sums
+	if (!rc && K == 1)                           // K == 1 takes its column sums from the count table (kmeans.cu)
+		rc = ensure_buf(h, &h->counts_dev, &h->counts_cap, (size_t) qvz_gpu_cond_counts_len(1, C) * sizeof(uint32_t));
 	if (rc) return rc;
 	h->k1_valid = 0;                             // a new run reads the rows again
+	h->counts_cached = 0;
 	if (!h->h_moved) QVZ_CUDA(h, cudaMallocHost(&h->h_moved, QVZ_MAX_K * sizeof(double)));
 	if (!h->h_counts) QVZ_CUDA(h, cudaMallocHost(&h->h_counts, QVZ_MAX_K * sizeof(int64_t)));
 	QVZ_CUDA(h, cudaMemcpyAsync(h->means_b, init_means, (size_t) K * C, cudaMemcpyHostToDevice, h->stream));
@@ -447,6 +451,7 @@ extern "C" int qvz_gpu_set_clusters(qvz_gpu *h, uint32_t K, const uint8_t *clust
 	if (!h->Xw) QVZ_FAIL(h, QVZ_ERR_ARG, "set_clusters: no rows loaded");
 	if (K == 0 || K > 255) QVZ_FAIL(h, QVZ_ERR_ARG, "set_clusters: bad cluster count");
 	QVZ_CUDA(h, cudaSetDevice(h->device));
+	h->counts_cached = 0;
 	int rc = pipeline_h2d(h, cluster_ids, 1, 1, [&](const piece &pc) {
 		return qvz_layout_ids_from_lines(h, pc.r0, pc.nr, h->stage[pc.buf]);
 	});
@@ -462,8 +467,15 @@ extern "C" int qvz_gpu_cond_counts_dev(qvz_gpu *h, uint32_t *counts_dev) {
 	if (!h->Xw || !h->K) QVZ_FAIL(h, QVZ_ERR_ARG, "cond_counts: rows and cluster ids must be resident first");
 	QVZ_CUDA(h, cudaSetDevice(h->device));
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
-	int rc = qvz_cond_counts_launch(h, counts_dev);
-	if (rc) return rc;
+	if (h->counts_cached && h->K == 1) {
+		// the K == 1 k-means pass of these rows already counted them (kmeans.cu): same table, no second pass
+		if (counts_dev != h->counts_dev)
+			QVZ_CUDA(h, cudaMemcpyAsync(counts_dev, h->counts_dev, (size_t) qvz_gpu_cond_counts_len(1, h->L.C) * sizeof(uint32_t),
+			                            cudaMemcpyDeviceToDevice, h->stream));
+	} else {
+		int rc = qvz_cond_counts_launch(h, counts_dev);
+		if (rc) return rc;
+	}
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
 	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
 	h->tm.cond_counts_ms = ev_ms(h, EV_A, EV_B);

@@ -247,53 +247,42 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
 }
 
 // K == 1: assign_cluster has nothing to compare -- every line lands in cluster 0 -- so one iteration is just
-// recalculate_means' column sums (src/cluster.c:96-104): a streaming reduction at HBM speed.
-// CTA <-> (chunk of slots, column word); a thread adds 16-byte vectors of 4 slots as packed 16-bit halves
-// (<= KS_ITERS * 4 * 255 < 2^16 per field), then warp REDUX + one 64-bit global atomic per (CTA, column).
-#define KS_THREADS 256
-#define KS_ITERS 32
-#define KS_CHUNK (KS_THREADS * 4 * KS_ITERS)
-
-__global__ void __launch_bounds__(KS_THREADS)
-qvz_kmeans_single_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t *__restrict__ cl,
-                         unsigned long long *__restrict__ sums)
+// recalculate_means' column sums (src/cluster.c:96-104).  Those sums are marginals of the conditional-count table
+// that calculate_statistics needs right after (sum over prev and value of (value + '!') * count), so the rows are
+// not read for k-means at all: the counting pass runs here, the exact integer sums are folded out of its table,
+// and qvz_gpu_cond_counts hands out the same table (abi.cu: counts_cached).  One pass over the rows serves both
+// stages; the sums are integers, so nothing about the centroids or the `moved` values changes.
+__global__ void __launch_bounds__(256)
+qvz_kmeans_k1_ids_kernel(uint64_t P, uint8_t *__restrict__ cl)
 {
-	__shared__ uint32_t red[KS_THREADS / 32][4];
-	const uint32_t c4 = blockIdx.y, tid = threadIdx.x;
-	const uint64_t p0 = (uint64_t) blockIdx.x * KS_CHUNK;
-	const uint64_t p1 = (p0 + KS_CHUNK < L.P) ? p0 + KS_CHUNK : L.P;      // P % 4096 == 0: whole uint4s
-	const uint4 *src = (const uint4 *) (Xw + (uint64_t) c4 * L.P);
-	uint32_t lo = 0, hi = 0;
-#pragma unroll 8
-	for (uint64_t p = p0 + 4 * tid; p < p1; p += 4 * KS_THREADS) {
-		uint4 v;
-		asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-		             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + (p >> 2)));
-		lo += (v.x & 0x00FF00FFu) + (v.y & 0x00FF00FFu) + (v.z & 0x00FF00FFu) + (v.w & 0x00FF00FFu);
-		hi += ((v.x >> 8) & 0x00FF00FFu) + ((v.y >> 8) & 0x00FF00FFu) + ((v.z >> 8) & 0x00FF00FFu) + ((v.w >> 8) & 0x00FF00FFu);
+	// line->cluster = 0 for every real line (0xFF marks an empty slot); ids are < 16, so bit 7 is set only in 0xFF
+	uint32_t *c32 = (uint32_t *) cl;
+	for (uint64_t p = ((uint64_t) blockIdx.x * 256 + threadIdx.x) * 4; p < P; p += (uint64_t) gridDim.x * 1024) {
+		const uint32_t v = c32[p >> 2];
+		const uint32_t nv = ((v >> 7) & 0x01010101u) * 0xFFu;
+		if (nv != v) c32[p >> 2] = nv;
 	}
-	if (c4 == 0) {                                   // line->cluster = 0 for every real line (0xFF marks an empty slot)
-		uint32_t *c32 = (uint32_t *) cl;
-		for (uint64_t p = p0 + 4 * tid; p < p1; p += 4 * KS_THREADS) {
-			const uint32_t v = c32[p >> 2];
-			const uint32_t nv = ((v >> 7) & 0x01010101u) * 0xFFu;      // ids are < 16: bit 7 is set only in 0xFF
-			if (nv != v) c32[p >> 2] = nv;
-		}
-	}
-	uint32_t f[4] = {lo & 0xFFFFu, hi & 0xFFFFu, lo >> 16, hi >> 16};   // bytes 0..3 of a word = columns 4*c4 .. 4*c4+3
-#pragma unroll
-	for (int j = 0; j < 4; ++j) {
-		const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, f[j]);
-		if ((tid & 31) == 0) red[tid >> 5][j] = s;
-	}
+}
+
+// one CTA per column: rows 1+(c-1)*72 .. +71 of the count table (row 0 for column 0), 72 counters each
+__global__ void __launch_bounds__(256)
+qvz_kmeans_k1_sums_kernel(uint32_t C, uint64_t n_lines, const uint32_t *__restrict__ counts,
+                          unsigned long long *__restrict__ sums)
+{
+	__shared__ unsigned long long red[8];
+	const uint32_t c = blockIdx.x, tid = threadIdx.x;
+	const uint32_t *rows = counts + (c ? (uint64_t) (1 + (c - 1) * 72) * 72 : 0);
+	const uint32_t cells = c ? 72u * 72u : 72u;
+	unsigned long long s = 0;
+	for (uint32_t i = tid; i < cells; i += 256) s += (unsigned long long) rows[i] * (i % 72u + 33u);
+	for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+	if ((tid & 31) == 0) red[tid >> 5] = s;
 	__syncthreads();
-	if (tid < 4 && 4 * c4 + tid < L.C) {
-		unsigned long long s = 0;
-#pragma unroll
-		for (int w = 0; w < KS_THREADS / 32; ++w) s += red[w][tid];
-		if (s) atomicAdd(&sums[4 * c4 + tid], s);
+	if (tid == 0) {
+		for (int w = 1; w < 8; ++w) s += red[w];
+		sums[c] = s;
+		if (c == 0) sums[C] = n_lines;               // cluster_t.count of the only cluster
 	}
-	if (blockIdx.x == 0 && c4 == 0 && tid == 0) sums[L.C] = L.n_lines;   // cluster_t.count of the only cluster
 }
 
 // recalculate_means (src/cluster.c:106-128) on the reduced sums; also repacks the centroids for dp4a.
@@ -379,14 +368,19 @@ int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev) {
 	if (K == 1) {
 		// With one cluster the assignment cannot change, so every iteration of this k-means run has the same
 		// column sums as the first one (the reference recomputes them; recalculate_means then finds moved == 0
-		// and stops, src/cluster.c:231-233).  The rows are read once per run; later iterations copy the sums.
+		// and stops, src/cluster.c:231-233).  The first iteration takes them from the count table (see above);
+		// later iterations copy the sums.
 		if (h->k1_valid) {
 			QVZ_CUDA(h, cudaMemcpyAsync(sums_dev, h->k1_sums, sum_bytes, cudaMemcpyDeviceToDevice, h->stream));
 			return QVZ_OK;
 		}
-		QVZ_CUDA(h, cudaMemsetAsync(sums_dev, 0, sum_bytes, h->stream));
-		dim3 g((unsigned) ((h->L.P + KS_CHUNK - 1) / KS_CHUNK), C4);
-		qvz_kmeans_single_kernel<<<g, KS_THREADS, 0, h->stream>>>(h->L, h->Xw, h->cl, (unsigned long long *) sums_dev);
+		qvz_kmeans_k1_ids_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(h->L.P, h->cl);
+		QVZ_LAUNCHED(h);
+		QVZ_CUDA(h, cudaGetLastError());
+		int rc = qvz_cond_counts_launch(h, h->counts_dev);           // abi.cu sized counts_dev in kmeans_begin
+		if (rc) return rc;
+		h->counts_cached = 1;
+		qvz_kmeans_k1_sums_kernel<<<h->L.C, 256, 0, h->stream>>>(h->L.C, h->L.n_lines, h->counts_dev, (unsigned long long *) sums_dev);
 		QVZ_LAUNCHED(h);
 		QVZ_CUDA(h, cudaGetLastError());
 		QVZ_CUDA(h, cudaMemcpyAsync(h->k1_sums, sums_dev, sum_bytes, cudaMemcpyDeviceToDevice, h->stream));

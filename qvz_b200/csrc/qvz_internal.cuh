@@ -69,6 +69,7 @@ struct qvz_gpu {
 	double *h_moved;         // pinned [QVZ_MAX_K]
 	int64_t *h_counts;       // pinned [QVZ_MAX_K] line counts
 	uint32_t *counts_dev;    // conditional-count table of the host-pointer entry point
+	int counts_cached;       // counts_dev holds the table of the resident rows and ids (left there by the K == 1 k-means pass)
 	size_t means_b_cap, means_w_cap, means_sq_cap, sums_cap, moved_cap, counts_cap;
 
 	// quantize state
