@@ -7,8 +7,8 @@
 
 #include "qvz_internal.cuh"
 
-#define QVZ_TARGET_RUNS (148u * 768u)      // runs per shard (3 draw-generator CTAs per SM): enough threads for the draw generator, few enough that the
-                                           // WELL jump-ahead (one F2 mat-vec per run) stays cheap
+#define QVZ_TARGET_RUNS (148u * 1024u)     // runs per shard (4 draw-generator CTAs per SM, a whole number of walk batches per step): enough threads for
+                                           // the draw generator, few enough that the WELL jump-ahead (one F2 mat-vec per run) stays cheap
 
 enum { EV_A = 0, EV_B, EV_C, EV_D, EV_E, EV_F };
 
@@ -18,6 +18,7 @@ static void free_dev(void *p) {
 
 static void release_rows(qvz_gpu *h) {
 	free_dev(h->Xw); h->Xw = nullptr; h->Xw_cap = 0;
+	free_dev(h->Xb); h->Xb = nullptr; h->Xb_cap = 0;
 	free_dev(h->cl); h->cl = nullptr; h->cl_cap = 0;
 	free_dev(h->run_states); h->run_states = nullptr; h->rs_cap = 0;
 	free_dev(h->Yw); h->Yw = nullptr; h->Yw_cap = 0;
@@ -34,7 +35,15 @@ static int ensure_buf(qvz_gpu *h, T **p, size_t *cap, size_t bytes) {
 	free_dev(*p);
 	*p = nullptr;
 	*cap = 0;
-	QVZ_CUDA(h, cudaMalloc(p, bytes));
+	cudaError_t e = cudaMalloc(p, bytes);
+	if (e == cudaErrorMemoryAllocation && h->Xb && (void *) p != (void *) &h->Xb) {
+		cudaGetLastError();                          // the optional byte planes give way to a buffer that is needed
+		free_dev(h->Xb);
+		h->Xb = nullptr;
+		h->Xb_cap = 0;
+		e = cudaMalloc(p, bytes);
+	}
+	QVZ_CUDA(h, e);
 	*cap = bytes;
 	return QVZ_OK;
 }
@@ -289,14 +298,25 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 	uint64_t target_runs = QVZ_TARGET_RUNS;
 	if (const char *e = getenv("QVZ_TARGET_RUNS")) target_runs = strtoull(e, nullptr, 10) ? strtoull(e, nullptr, 10) : target_runs;   // tuning knob
 	uint64_t lr = (n_lines + target_runs - 1) / target_runs;
-	lr = (lr + 15) & ~15ull;                      // multiple of 4: runs start on WELL word boundaries; of 16: P % 4096 == 0
-	if (lr < 16) lr = 16;
+	lr = (lr + 3) & ~3ull;                        // multiple of 4: every run starts on a WELL word boundary (T % 4096 == 0 gives P % 4096 == 0)
+	if (lr < 4) lr = 4;
 	L.Lr = (uint32_t) lr;
 	uint64_t runs = (n_lines + lr - 1) / lr;
 	L.T = (uint32_t) ((runs + QVZ_RUN_ALIGN - 1) / QVZ_RUN_ALIGN * QVZ_RUN_ALIGN);
 	L.P = (uint64_t) L.T * L.Lr;
 
 	int rc = ensure_buf(h, &h->Xw, &h->Xw_cap, (size_t) L.C4 * L.P * sizeof(uint32_t));
+	if (!rc && !getenv("QVZ_NO_PLANES")) {
+		// second copy as byte planes for the one-cluster counting pass (cond_counts.cu); optional: without it
+		// (no memory left, or switched off) the word-column kernel counts
+		if (ensure_buf(h, &h->Xb, &h->Xb_cap, (size_t) L.C * L.P) != QVZ_OK) {
+			cudaGetLastError();
+			h->Xb = nullptr;
+			h->Xb_cap = 0;
+		}
+	} else if (!rc) {
+		free_dev(h->Xb); h->Xb = nullptr; h->Xb_cap = 0;
+	}
 	if (rc) return rc;
 	rc = ensure_buf(h, &h->cl, &h->cl_cap, (size_t) L.P);
 	if (rc) return rc;
@@ -565,7 +585,8 @@ static int upload_tables(qvz_gpu *h, const struct qvz_flat_tables *t, int *toepl
 static int start_draws(qvz_gpu *h, const uint32_t seed[32], bool with_draws) {
 	const qvz_layout &L = h->L;
 	int rc = ensure_buf(h, &h->run_states, &h->rs_cap, (size_t) L.T * 32 * sizeof(uint32_t));
-	if (!rc && with_draws) rc = ensure_buf(h, &h->Dw, &h->Dw_cap, (size_t) L.C4 * L.P * sizeof(uint32_t));
+	// draw words of a run in sequence order, Lr*C/4 rows of T words (quantize.cu); the walk reads up to two rows ahead
+	if (!rc && with_draws) rc = ensure_buf(h, &h->Dw, &h->Dw_cap, ((size_t) L.Lr * L.C / 4 + 2) * L.T * sizeof(uint32_t));
 	if (rc) return rc;
 	if (h->walk_recorded) QVZ_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->ev_walk_done, 0));   // the last walk still reads Dw
 	cudaStream_t main_stream = h->stream;

@@ -104,9 +104,165 @@ qvz_cond_counts_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint
 	}
 }
 
+// ---- one cluster (the reference's default, -c 1): lane-private counters over byte planes
+//
+// With K == 1 a slice is A x A counters, and for Phred+33 data with Q <= 41 (A = 42) thirty-two copies of it fit the
+// 227 KB of shared memory: copy l lives entirely in bank l and is only ever touched by lane l, so every warp-wide
+// atomic is conflict-free (one wavefront instead of ~3.3 for 32 random addresses; ATOMS across warps stay atomic).
+// That needs one column per CTA at a time, so this kernel reads the rows as byte planes Xb[c][p] (kept next to Xw at
+// ingest): 16 slots of column c and of column c-1 per thread and iteration (two 16-byte loads for 16 symbols; the
+// plane of column c is read again as `prev` by the CTA working one column ahead at the same slots, an L2 hit).
+// Work is cut into equal contiguous spans of the (column, slot) sequence, one per SM: a CTA crosses at most two
+// column boundaries, where it reduces its 32 copies (one global atomic per non-zero counter) and clears them.
+#define CP_THREADS 1024
+#define CP_SLOTS 16u                            // slots per thread and iteration
+#define CP_BLOCK (CP_THREADS * CP_SLOTS)        // slots per CTA iteration
+
+__device__ __forceinline__ uint4 cp_ldg128(const uint8_t *p) {
+	uint4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+
+// four slots of one column: byte b of cw = value, byte b of pw = previous column's value (raw ASCII).
+// CHECK = some of the 16 slots of this thread hold no line (zero bytes): test every byte.
+template <bool CHECK>
+__device__ __forceinline__ void cp_count_word(uint32_t cw, uint32_t pw, uint32_t coef, int bias, uint32_t lane_addr)
+{
+#pragma unroll
+	for (uint32_t b = 0; b < 4; ++b) {
+		if (!CHECK || ((cw >> (8 * b)) & 0xFFu)) {
+			const uint32_t r = __byte_perm(cw, pw, b | ((4 + b) << 4) | 0x8800u);       // value | prev << 8 (bytes < 128: upper bytes 0)
+			const uint32_t idx = (uint32_t) __dp4a((int) r, (int) coef, bias);          // (prev-33)*A + (value-33)
+			cc_red_shared(lane_addr + idx * 128u, 1u);
+		}
+	}
+}
+
+__device__ __forceinline__ uint32_t cp_zero_bytes(uint32_t w) { return (w - 0x01010101u) & ~w & 0x80808080u; }
+
+// 16 slots of one column (cw) and of the column before it (pw)
+__device__ __forceinline__ void cp_count16(const uint4 &cw, const uint4 &pw, uint32_t coef, int bias, uint32_t lane_addr)
+{
+	if ((cp_zero_bytes(cw.x) | cp_zero_bytes(cw.y) | cp_zero_bytes(cw.z) | cp_zero_bytes(cw.w)) == 0u) {   // 16 real lines
+		cp_count_word<false>(cw.x, pw.x, coef, bias, lane_addr);
+		cp_count_word<false>(cw.y, pw.y, coef, bias, lane_addr);
+		cp_count_word<false>(cw.z, pw.z, coef, bias, lane_addr);
+		cp_count_word<false>(cw.w, pw.w, coef, bias, lane_addr);
+	} else {
+		cp_count_word<true>(cw.x, pw.x, coef, bias, lane_addr);
+		cp_count_word<true>(cw.y, pw.y, coef, bias, lane_addr);
+		cp_count_word<true>(cw.z, pw.z, coef, bias, lane_addr);
+		cp_count_word<true>(cw.w, pw.w, coef, bias, lane_addr);
+	}
+}
+
+// n blocks of one column for this thread, two in flight (the loads of the next block are issued before the
+// atomics of the current one).  FIRST = column 0: the previous value is 0 for every line (-> pmfs[0]).
+template <bool FIRST>
+__device__ __forceinline__ void cp_segment(const uint8_t *pc, uint64_t P, uint32_t n, uint32_t coef, int bias, uint32_t lane_addr)
+{
+	const uint4 bang = make_uint4(0x21212121u, 0x21212121u, 0x21212121u, 0x21212121u);
+	if (n == 0) return;
+	const uint8_t *pp = pc - P;
+	uint4 a = cp_ldg128(pc), ap = bang, b, bp = bang;
+	if (!FIRST) ap = cp_ldg128(pp);
+	uint32_t k = 0;
+	for (; k + 2 <= n; k += 2) {
+		b = cp_ldg128(pc + CP_BLOCK);
+		if (!FIRST) bp = cp_ldg128(pp + CP_BLOCK);
+		pc += 2 * CP_BLOCK;
+		pp += 2 * CP_BLOCK;
+		cp_count16(a, ap, coef, bias, lane_addr);
+		if (k + 2 < n) {
+			a = cp_ldg128(pc);
+			if (!FIRST) ap = cp_ldg128(pp);
+		}
+		cp_count16(b, bp, coef, bias, lane_addr);
+	}
+	if (k < n) cp_count16(a, ap, coef, bias, lane_addr);
+}
+
+__global__ void __launch_bounds__(CP_THREADS, 1)
+qvz_cond_counts_planes_kernel(qvz_layout L, const uint8_t *__restrict__ Xb, uint32_t A, uint32_t S, uint32_t *__restrict__ counts)
+{
+	extern __shared__ uint32_t hist[];           // [A*A][32]: counter (prev, value) of lane l at word (prev*A + value)*32 + l
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t cells = A * A;
+	for (uint32_t i = tid; i < cells * 32; i += CP_THREADS) hist[i] = 0;
+	__syncthreads();
+
+	const uint64_t nblk = (L.P + CP_BLOCK - 1) / CP_BLOCK;              // CTA iterations per column
+	const uint32_t lane_addr = (uint32_t) __cvta_generic_to_shared(hist) + lane * 4u;
+	const uint32_t coef = 1u | (A << 8);
+	const int bias = -33 * (int) (A + 1);
+
+	auto flush = [&](uint32_t col) {             // 32 copies -> pmfs[] rows of this column, then clear
+		__syncthreads();
+		for (uint32_t cell = warp; cell < cells; cell += CP_THREADS / 32) {
+			const uint32_t v = hist[cell * 32 + lane];
+			if (__any_sync(0xFFFFFFFFu, v != 0u)) {
+				hist[cell * 32 + lane] = 0;
+				const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, v);
+				if (lane == 0) {
+					const uint32_t prev = cell / A, cur = cell - prev * A;
+					atomicAdd(counts + (col ? (uint64_t) (1 + (col - 1) * 72 + prev) * 72 : 0) + cur, s);
+				}
+			}
+		}
+		__syncthreads();
+	};
+
+	const uint64_t toff = (uint64_t) tid * CP_SLOTS;
+	auto job = [&](uint32_t col, uint64_t blk, uint64_t bend) {          // blocks [blk, bend) of one column, then flush
+		const uint8_t *pc = Xb + (uint64_t) col * L.P + blk * CP_BLOCK + toff;
+		// P % 4096 == 0: a thread's 16 slots are all inside the plane or all outside (last block of a column only)
+		uint32_t n = (uint32_t) (bend - blk);
+		if (n && bend == nblk && (nblk - 1) * CP_BLOCK + toff >= L.P) n -= 1;
+		if (col) cp_segment<false>(pc, L.P, n, coef, bias, lane_addr);
+		else cp_segment<true>(pc, L.P, n, coef, bias, lane_addr);
+		flush(col);
+	};
+	// Neighbouring CTAs work on neighbouring columns at the same slots at the same time, so the plane a CTA reads as
+	// `prev` is the one its neighbour is reading as `value` (one HBM read, one L2 hit).  First whole columns, one per
+	// CTA and round; then the columns that are left, cut into S pieces each and dealt round-robin, column fastest.
+	const uint32_t G = gridDim.x, rounds = L.C / G, rem = L.C - rounds * G;
+	for (uint32_t r = 0; r < rounds; ++r) job(r * G + blockIdx.x, 0, nblk);
+	for (uint64_t id = blockIdx.x; id < (uint64_t) S * rem; id += G) {
+		const uint64_t sp = id / rem;
+		const uint32_t j = (uint32_t) (id - sp * rem);
+		job(rounds * G + j, sp * nblk / S, (sp + 1) * nblk / S);
+	}
+}
+
+// largest alphabet box whose 32 lane-private copies fit shared memory (42: Phred+33 with Q <= 41)
+static bool planes_possible(const qvz_gpu *h, uint32_t A) {
+	return h->K == 1 && h->Xb && (size_t) A * A * 128 <= 226 * 1024 && !getenv("QVZ_COUNTS_WORDS");
+}
+
 int qvz_cond_counts_launch(qvz_gpu *h, uint32_t *counts_dev) {
 	const uint32_t K = h->K;
 	const uint32_t A = h->smax + 1 > 72 ? 72 : h->smax + 1;
+	if (planes_possible(h, A)) {
+		const size_t smem = (size_t) A * A * 128;
+		QVZ_CUDA(h, cudaMemsetAsync(counts_dev, 0, qvz_gpu_cond_counts_len(1, h->L.C) * sizeof(uint32_t), h->stream));
+		QVZ_CUDA(h, cudaFuncSetAttribute(qvz_cond_counts_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		// pieces per left-over column: fewest waves of (piece + flush), the flush costing about 3 blocks of counting
+		const uint64_t G = (uint64_t) h->sm_count, rem = h->L.C % G, nblk = (h->L.P + CP_BLOCK - 1) / CP_BLOCK;
+		uint32_t S = 1;
+		double best = 0.0;
+		for (uint32_t c = 1; rem && c <= 256 && c <= nblk; ++c) {
+			const double cost = (double) ((c * rem + G - 1) / G) * ((double) nblk / c + 3.0);
+			if (c == 1 || cost < best) {
+				best = cost;
+				S = c;
+			}
+		}
+		qvz_cond_counts_planes_kernel<<<h->sm_count, CP_THREADS, smem, h->stream>>>(h->L, h->Xb, A, S, counts_dev);
+		QVZ_LAUNCHED(h);
+		QVZ_CUDA(h, cudaGetLastError());
+		return QVZ_OK;
+	}
 	const size_t slice_bytes = ((size_t) A * A + CC_PAD) * sizeof(uint32_t);
 	uint32_t G = (uint32_t) ((200 * 1024) / (4 * slice_bytes));       // clusters per pass that fit shared memory (2 at A = 72, 7 at A = 42)
 	if (G > K) G = K;

@@ -28,7 +28,7 @@ __device__ __forceinline__ bool range_slot(const qvz_layout &L, const run_range 
 // writes packed words coalesced across the warp.  Slots past the last line get zero words and id 0xFF.
 __global__ void __launch_bounds__(QVZ_THREADS)
 qvz_ingest_kernel(qvz_layout L, run_range R, const uint8_t *__restrict__ stage, uint32_t row_stride,
-                  uint32_t *__restrict__ Xw, uint8_t *__restrict__ cl, int *__restrict__ flags)
+                  uint32_t *__restrict__ Xw, uint8_t *__restrict__ Xb, uint8_t *__restrict__ cl, int *__restrict__ flags)
 {
 	uint64_t p, line;
 	if (!range_slot(L, R, (uint64_t) blockIdx.x * QVZ_THREADS + threadIdx.x, p, line)) return;
@@ -51,6 +51,11 @@ qvz_ingest_kernel(qvz_layout L, run_range R, const uint8_t *__restrict__ stage, 
 			}
 		}
 		Xw[(uint64_t) c4 * L.P + p] = w;
+		if (Xb) {                                    // the same bytes as one plane per column (zero = no line)
+#pragma unroll
+			for (uint32_t j = 0; j < 4; ++j)
+				if (4 * c4 + j < L.C) Xb[(uint64_t) (4 * c4 + j) * L.P + p] = (uint8_t) (w >> (8 * j));
+		}
 	}
 	cl[p] = valid ? 0 : QVZ_NO_LINE;
 	if (bad) atomicOr(&flags[0], 1);
@@ -116,7 +121,7 @@ static inline run_range make_range(const qvz_gpu *h, uint32_t r0, uint32_t nr) {
 
 int qvz_layout_ingest(qvz_gpu *h, uint32_t r0, uint32_t nr, const uint8_t *stage_dev, uint32_t row_stride) {
 	qvz_ingest_kernel<<<range_blocks(h, nr), QVZ_THREADS, 0, h->stream>>>(h->L, make_range(h, r0, nr), stage_dev, row_stride,
-	                                                                       h->Xw, h->cl, h->flags);
+	                                                                       h->Xw, h->Xb, h->cl, h->flags);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;

@@ -285,11 +285,10 @@ int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int dmode) {
 //
 //   qvz_draws_kernel      thread <-> run.  The WELL1024a state lives in 32 REGISTERS: the generator is
 //                         unrolled over one full turn of the ring (32 steps, n returns to 0) so that every
-//                         state index is a compile-time constant; the 32 words of a turn are expanded to
-//                         one byte per 7-bit draw and parked in a per-thread shared-memory FIFO, from which
-//                         the reference's bit server order (4 draws per word, low bits first, src/well.c:33-46)
-//                         is replayed line by line into Dw[c4][p], one byte per (line, column), packed like
-//                         the rows (coalesced: adjacent threads hold adjacent slots).
+//                         state index is a compile-time constant; each word is expanded to one byte per
+//                         7-bit draw in the reference's bit server order (4 draws per word, low bits first,
+//                         src/well.c:33-46) and stored in SEQUENCE order, Dw[w*T + run] (coalesced: adjacent
+//                         threads are adjacent runs).  Line i of a run starts at draw i*C: the walk realigns.
 //   qvz_quantize_batched  one CTA walks QB_LINES slots column-synchronously.  The (cluster, column) tables
 //                         are COMPACTED to the A x A box of values that can occur (A-1 = largest symbol /
 //                         quantized value present) and staged per column group in shared memory by TMA bulk
@@ -317,6 +316,7 @@ int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int dmode) {
 #endif
 #define QB_LPT 4
 #define QB_LINES (QB_THREADS * QB_LPT)
+static_assert(QVZ_RUN_ALIGN % QB_LINES == 0, "a step (T slots) must be a whole number of walk batches");
 #define QB_POISON 72u
 
 // ---- draw generator ------------------------------------------------------------------------------------
@@ -340,137 +340,31 @@ __device__ __forceinline__ uint32_t well_expand_draws(uint32_t w) {
 	return u + (u & 0x3F803F80u);                        // draws 1, 3 move up by 1 more bit
 }
 
-template <int T>
-__device__ __forceinline__ void well_turn(uint32_t (&s)[32], uint32_t *fifo) {
-	if constexpr (T < 32) {
-		fifo[T * QZ_THREADS] = well_expand_draws(well_step_reg<T>(s));
-		well_turn<T + 1>(s, fifo);
-	}
-}
-
-__global__ void __launch_bounds__(QZ_THREADS)
-qvz_draws_kernel(qvz_layout L, const uint32_t *__restrict__ run_states, uint32_t *__restrict__ Dw)
-{
-	__shared__ uint32_t fifo_s[QZ_WS_WORDS];             // [32][256]: one turn of draw words per thread
-	const uint32_t t = threadIdx.x;
-	const uint64_t r = (uint64_t) blockIdx.x * QZ_THREADS + t;
-	uint32_t s[32];
-#pragma unroll
-	for (int k = 0; k < 32; ++k) s[k] = run_states[r * 32 + k];
-	uint32_t *fifo = fifo_s + t;
-	uint32_t pos = 32;                                   // FIFO read position (uniform); 32 = empty
-	uint32_t ch = 0, nb = 0;                             // carry: the top nb bytes of ch are the next undrawn draws (nb uniform)
-	const uint32_t C = L.C, full = C >> 2, rem = C & 3;
-	const uint32_t rmask = (1u << (8 * rem)) - 1u;
-	auto pop = [&]() -> uint32_t {
-		if (pos == 32) {
-			well_turn<0>(s, fifo);
-			pos = 0;
-		}
-		return fifo[(pos++) * QZ_THREADS];               // thread-private column: no barrier needed
-	};
-	for (uint32_t i = 0; i < L.Lr; ++i) {
-		uint32_t *dp = Dw + (uint64_t) i * L.T + r;
-		const uint32_t sh = 32 - 8 * nb;                 // constant along a line: every full word takes 4 bytes and adds 4
-		for (uint32_t c4 = 0; c4 < full; ++c4) {
-			const uint32_t w = pop();
-			st_stream_u32(dp, __funnelshift_rc(ch, w, sh));
-			ch = w;
-			dp += L.P;
-		}
-		if (rem) {                                       // last, partial word of the line
-			uint32_t v;
-			if (nb >= rem) {
-				v = ch >> sh;
-				nb -= rem;
-			} else {
-				const uint32_t w = pop();
-				v = __funnelshift_rc(ch, w, sh);
-				ch = w;
-				nb += 4 - rem;
-			}
-			st_stream_u32(dp, v & rmask);
-		}
-	}
-}
-
-// The same generator without the FIFO, for lines of at least one full word (C >= 4): every word is consumed in the
-// unrolled step that produced it.  All bookkeeping (full words left in the line, carried draws, line index) is
-// uniform across the grid -- every thread is at the same offset of its own run -- so the branches cost no divergence.
-struct dr_state {
-	uint32_t *dp;        // Dw word of the current line that is written next (per thread)
-	uint32_t ch;         // last WELL word (expanded): its top nb bytes are draws not yet consumed (per thread)
-	uint32_t nb, sh;     // carried draws and the funnel shift 32 - 8*nb of the current line (uniform)
-	uint32_t wleft;      // full words left in the current line; 0 = the line waits for its partial last word (uniform)
-	uint32_t i;          // current line of the run (uniform)
-};
-
-// everything that happens once per line (last full word, partial word, line change): out of line on purpose, so that the
-// 32-step unrolled turn stays small enough for the instruction cache
-__device__ __noinline__ dr_state draws_line_end(dr_state d, uint32_t w, uint32_t *Dw, uint64_t r, uint32_t T, uint64_t P,
-                                                 uint32_t full, uint32_t rem, uint32_t rmask) {
-	bool advance = false;
-	if (d.wleft) {                                   // the last full word of the line
-		st_stream_u32(d.dp, __funnelshift_rc(d.ch, w, d.sh));
-		d.ch = w;
-		d.dp += P;
-		d.wleft = 0;
-		if (rem == 0) advance = true;
-		else if (d.nb >= rem) {                      // its partial word is already in the carry
-			st_stream_u32(d.dp, (d.ch >> d.sh) & rmask);
-			d.nb -= rem;
-			advance = true;
-		}
-	} else {                                         // the partial last word needed this new word
-		st_stream_u32(d.dp, __funnelshift_rc(d.ch, w, d.sh) & rmask);
-		d.ch = w;
-		d.nb += 4 - rem;
-		advance = true;
-	}
-	if (advance) {
-		d.i += 1;
-		d.dp = Dw + (uint64_t) d.i * T + r;
-		d.wleft = full;
-		d.sh = 32 - 8 * d.nb;
-	}
-	return d;
-}
-
-template <int T>
-__device__ __forceinline__ void well_turn_direct(uint32_t (&s)[32], dr_state &d, const qvz_layout &L, uint32_t *Dw, uint64_t r,
-                                                 uint32_t full, uint32_t rem, uint32_t rmask) {
+// One turn of the ring: 32 steps, 32 draw words.  Dw holds the draws of a run in SEQUENCE order -- word w of run r
+// (draws 4w .. 4w+3 after the run's first draw) at Dw[w*T + r] -- so the generator does no per-line bookkeeping at
+// all (adjacent threads = adjacent runs: coalesced stores); the walk realigns on read, where a line starts at draw
+// i*C of its run, i.e. at byte (i*C)&3 of word (i*C)>>2.  GUARD = the last, partial turn of the run.
+template <int T, bool GUARD>
+__device__ __forceinline__ void well_turn_seq(uint32_t (&s)[32], uint32_t *&dp, uint64_t stride, uint32_t left) {
 	if constexpr (T < 32) {
 		const uint32_t w = well_expand_draws(well_step_reg<T>(s));
-		if (d.i < L.Lr) {                                // words past the end of the run (last turn only) are dropped
-			if (d.wleft > 1) {                           // the common case: a full word that is not the line's last
-				st_stream_u32(d.dp, __funnelshift_rc(d.ch, w, d.sh));
-				d.ch = w;
-				d.dp += L.P;
-				d.wleft -= 1;
-			} else d = draws_line_end(d, w, Dw, r, L.T, L.P, full, rem, rmask);
-		}
-		well_turn_direct<T + 1>(s, d, L, Dw, r, full, rem, rmask);
+		if (!GUARD || (uint32_t) T < left) st_stream_u32(dp, w);
+		dp += stride;
+		well_turn_seq<T + 1, GUARD>(s, dp, stride, left);
 	}
 }
 
-__global__ void __launch_bounds__(QZ_THREADS)
-qvz_draws_direct_kernel(qvz_layout L, const uint32_t *__restrict__ run_states, uint32_t *__restrict__ Dw)
+__global__ void __launch_bounds__(QZ_THREADS, 4)
+qvz_draws_kernel(qvz_layout L, const uint32_t *__restrict__ run_states, uint32_t *__restrict__ Dw)
 {
 	const uint64_t r = (uint64_t) blockIdx.x * QZ_THREADS + threadIdx.x;
 	uint32_t s[32];
 #pragma unroll
 	for (int k = 0; k < 32; ++k) s[k] = run_states[r * 32 + k];
-	const uint32_t C = L.C, full = C >> 2, rem = C & 3;
-	const uint32_t rmask = (1u << (8 * rem)) - 1u;
-	dr_state d;
-	d.dp = Dw + r;
-	d.ch = 0;
-	d.nb = 0;
-	d.sh = 32;
-	d.wleft = full;
-	d.i = 0;
-	const uint32_t turns = (uint32_t) (((uint64_t) L.Lr * C / 4 + 31) / 32);     // Lr % 16 == 0: whole words
-	for (uint32_t t = 0; t < turns; ++t) well_turn_direct<0>(s, d, L, Dw, r, full, rem, rmask);
+	const uint32_t words = (uint32_t) ((uint64_t) L.Lr * L.C / 4);       // Lr % 4 == 0: whole words
+	uint32_t *dp = Dw + r;
+	for (uint32_t t = 0; t < words / 32; ++t) well_turn_seq<0, false>(s, dp, L.T, 0);
+	if (words & 31) well_turn_seq<0, true>(s, dp, L.T, words & 31);
 }
 
 // largest quantized value any present context can emit for a data value <= smax  -> flags[4]
@@ -602,9 +496,15 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 	};
 
 	bool missing = false;
-	const uint64_t nbatch = L.P / QB_LINES;
+	// A batch = QB_LINES consecutive slots of ONE step i (slot = i*T + run; T % QB_LINES == 0, abi.cu): all its lines start
+	// at the same draw i*C of their runs, so the position in the draw stream is uniform across the CTA.
+	const uint32_t bps = L.T / QB_LINES;                 // batches per step
+	const uint64_t nbatch = (uint64_t) bps * L.Lr;
 	for (uint64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
-		const uint64_t pbase = batch * QB_LINES + tid;   // line j of this thread: slot pbase + j*QB_THREADS
+		const uint32_t step = (uint32_t) (batch / bps), boff = (uint32_t) (batch - (uint64_t) step * bps) * QB_LINES;
+		const uint64_t pbase = (uint64_t) step * L.T + boff + tid;
+		const uint32_t d0 = step * C;                    // first draw of these lines within their runs
+		const uint32_t dsh = 8 * (d0 & 3);               // ... = byte d0 & 3 of word d0 >> 2
 		uint32_t koff[QB_LPT], vprev[QB_LPT], erri[QB_LPT];
 		double errd[QB_LPT];
 		bool valid[QB_LPT];
@@ -620,35 +520,43 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			errd[j] = 0.0;
 		}
 		if (tid == 0) stage(0, gcount);
-		uint32_t xn[QB_LPT], dn[QB_LPT];
-		const uint32_t *xr = Xw + pbase, *drw = Dw + pbase;      // running pointers: one word column (P slots) per step
+		uint32_t xn[QB_LPT], da[QB_LPT], db[QB_LPT];     // draw words w, w+1 of the current step: da is the lower one in even steps, db in odd steps
+		const uint32_t *xr = Xw + pbase;                 // running pointer: one word column (P slots) per step
+		const uint32_t *drw = Dw + (uint64_t) (d0 >> 2) * L.T + (boff + tid);      // one draw word (T runs) per step
 		uint32_t *yr = Yw + pbase, *qr = WANT_QV ? Qw + pbase : nullptr;
 #pragma unroll
 		for (int j = 0; j < QB_LPT; ++j) {
 			xn[j] = ld_stream_u32(xr + j * QB_THREADS);
-			dn[j] = ld_stream_u32(drw + j * QB_THREADS);
+			da[j] = ld_stream_u32(drw + j * QB_THREADS);
+			db[j] = ld_stream_u32(drw + L.T + j * QB_THREADS);      // Dw has spare word rows at the end (abi.cu)
 		}
+		drw += 2 * (uint64_t) L.T;
 		// one data word (4 columns) of the QB_LPT lines of this thread; TAIL = the last, partial word
-		auto word = [&](uint32_t c4, auto tail_tag) {
+		// ODD alternates from word to word: the draw word that was the lower one is dead after the realignment and
+		// receives the load for the next step, so no loaded value is ever copied (a copy would wait for the load)
+		auto word = [&](uint32_t c4, auto tail_tag, auto odd_tag) {
 			constexpr bool TAIL = decltype(tail_tag)::value;
+			constexpr bool ODD = decltype(odd_tag)::value;
+			uint32_t (&dlo)[QB_LPT] = ODD ? db : da;
+			uint32_t (&dhi)[QB_LPT] = ODD ? da : db;
 			uint32_t x[QB_LPT], dr[QB_LPT], outw[QB_LPT], qvw[QB_LPT];
 #pragma unroll
 			for (int j = 0; j < QB_LPT; ++j) {
 				// raw ASCII bytes index the tables directly: the -33 is folded into the table base below.  A slot without
 				// a line (zero words) walks symbol 0 so that every lookup stays inside the tables; nothing of it is kept.
 				x[j] = valid[j] ? xn[j] : 0x21212121u;
-				dr[j] = dn[j];
+				dr[j] = __funnelshift_r(dlo[j], dhi[j], dsh);    // draws d0 + 4*c4 .. +3 of the run
 				outw[j] = 0;
 				qvw[j] = 0;
 			}
 			if (!TAIL) {                                 // next word's rows and draws: in flight during this word
 				xr += L.P;
-				drw += L.P;
 #pragma unroll
 				for (int j = 0; j < QB_LPT; ++j) {
 					xn[j] = ld_stream_u32(xr + j * QB_THREADS);
-					dn[j] = ld_stream_u32(drw + j * QB_THREADS);
+					dlo[j] = ld_stream_u32(drw + j * QB_THREADS);
 				}
+				drw += L.T;
 			}
 #pragma unroll
 			for (int g = 0; g < 4 / S; ++g) {            // the column groups (= staged images) inside this word
@@ -696,8 +604,15 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 				qr += L.P;
 			}
 		};
-		for (uint32_t c4 = 0; c4 + 1 < C4; ++c4) word(c4, std::false_type{});
-		word(C4 - 1, std::true_type{});
+		uint32_t c4 = 0;
+		for (; c4 + 2 < C4; c4 += 2) {
+			word(c4, std::false_type{}, std::false_type{});
+			word(c4 + 1, std::false_type{}, std::true_type{});
+		}
+		if (c4 + 1 < C4) {
+			word(c4, std::false_type{}, std::false_type{});
+			word(c4 + 1, std::true_type{}, std::true_type{});
+		} else word(c4, std::true_type{}, std::false_type{});
 #pragma unroll
 		for (int j = 0; j < QB_LPT; ++j) {
 			if (DMODE == 2) missing |= valid[j] && erri[j] >= 0x80000000u;
@@ -721,10 +636,7 @@ uint32_t qvz_quantize_batched_group(uint32_t K, uint32_t A) {
 }
 
 int qvz_quantize_draws(qvz_gpu *h) {
-	if (h->L.C >= 4 && !getenv("QVZ_DRAWS_FIFO"))
-		qvz_draws_direct_kernel<<<h->L.T / QZ_THREADS, QZ_THREADS, 0, h->stream>>>(h->L, h->run_states, h->Dw);
-	else                                             // lines shorter than a WELL word: the general byte-server replay
-		qvz_draws_kernel<<<h->L.T / QZ_THREADS, QZ_THREADS, 0, h->stream>>>(h->L, h->run_states, h->Dw);
+	qvz_draws_kernel<<<h->L.T / QZ_THREADS, QZ_THREADS, 0, h->stream>>>(h->L, h->run_states, h->Dw);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;
@@ -751,7 +663,7 @@ static void launch_batched(qvz_gpu *h, uint32_t K, uint32_t A) {
 	auto kern = qvz_quantize_batched_kernel<DMODE, WANT_QV, S>;
 	const size_t smem = batched_smem(K, A, S);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-	const uint64_t nbatch = h->L.P / QB_LINES;
+	const uint64_t nbatch = (uint64_t) (h->L.T / QB_LINES) * h->L.Lr;     // T % QB_LINES == 0 (QVZ_RUN_ALIGN)
 	const uint64_t resident = (uint64_t) h->sm_count * QB_CTAS;
 	const unsigned grid = (unsigned) (nbatch < resident ? nbatch : resident);
 	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->G, h->R, h->D, K, A, h->Yw,

@@ -3,7 +3,7 @@
 // Device-resident data layout:
 //
 //   slot p  <->  line n :   the shard's lines are cut into T "runs" of Lr consecutive lines
-//                           (Lr % 16 == 0: every run starts on a WELL word boundary and P % 4096 == 0);
+//                           (Lr % 4 == 0: every run starts on a WELL word boundary; T % 4096 == 0, so P % 4096 == 0);
 //                           run r, step i  =  line r*Lr + i  =  slot p = i*T + r.
 //                           Thread r of the quantize kernel walks run r sequentially, so its WELL1024a
 //                           stream is one contiguous piece of the reference's draw stream, while
@@ -20,7 +20,7 @@
 #include "../../include/qvz_gpu.h"
 
 #define QVZ_THREADS 256
-#define QVZ_RUN_ALIGN 256     // runs per shard are a multiple of this (one CTA of the draw generator); Lr % 16 == 0 => P % 4096 == 0
+#define QVZ_RUN_ALIGN 4096    // runs per shard are a multiple of this: one batch of the walk = 4096 slots of ONE step (quantize.cu), P % 4096 == 0
 #define QVZ_NFLAGS 8
 #define QVZ_NO_LINE 0xFFu
 #define QVZ_MAX_K 16            // register-resident distances in the k-means kernel
@@ -30,7 +30,7 @@ struct qvz_layout {
 	uint64_t first_line; // global index of line 0 of the shard
 	uint32_t C;          // columns
 	uint32_t C4;         // ceil(C/4) words per line
-	uint32_t Lr;         // lines per run (multiple of 16)
+	uint32_t Lr;         // lines per run (multiple of 4)
 	uint32_t T;          // runs (multiple of QVZ_THREADS)
 	uint64_t P;          // slots = T * Lr
 };
@@ -50,6 +50,7 @@ struct qvz_gpu {
 
 	qvz_layout L;
 	uint32_t *Xw;            // [C4][P]
+	uint8_t *Xb;             // [C][P] the same rows as one byte plane per column (cond_counts.cu, K == 1); nullptr = not kept
 	uint8_t *cl;             // [P]
 	uint32_t K;              // clusters currently installed in cl (0 = none)
 	int *flags;              // device [8]: 0 symbol range, 1 empty cluster, 2 missing context, 3 malformed tables,
@@ -81,7 +82,7 @@ struct qvz_gpu {
 	size_t flat_cap;
 	uint32_t *run_states;    // [T][32] WELL state (n = 0 frame) at the first draw of each run
 	uint32_t *Yw, *Qw;       // [C4][P] packed outputs (state|hi<<7, qv+33)
-	uint32_t *Dw;            // [C4][P] packed 7-bit WELL draws, one byte per (line, column)
+	uint32_t *Dw;            // [Lr*C/4 (+2)][T] the 7-bit WELL draws of every run in sequence order, one byte per draw
 	uint8_t *G;              // compact tables, one image per column: entry[K][A][A] of 8 bytes (quantize.cu)
 	size_t G_cap;
 	uint32_t smax;           // largest symbol value in the resident rows
@@ -99,6 +100,7 @@ struct qvz_gpu {
 	uint8_t *stage[2];
 	size_t stage_bytes;
 	cudaEvent_t ev_copied[2], ev_consumed[2];
+	size_t Xb_cap;
 	size_t Xw_cap, cl_cap, Yw_cap, Qw_cap, Dw_cap, Ep_cap, rs_cap;
 
 	// events / timings

@@ -16,6 +16,8 @@ __global__ void k(uint32_t *out, const uint32_t *idx, int iters, unsigned long l
 		else if (PAT == 1) w = lane + 32 * j;                 // 32 distinct banks
 		else if (PAT == 2) w = idx[(threadIdx.x * 8 + j) & 8191] & 8191;   // random
 		else if (PAT == 3) w = (lane & 7) * 33 + j * 300;     // 8 distinct addresses, 4 lanes each, distinct banks
+		else if (PAT == 5) w = lane + 32 * (idx[(threadIdx.x * 8 + j) & 8191] & 255);   // lane-private bank, random row per lane
+		else if (PAT == 6) w = lane + 32 * ((idx[(threadIdx.x * 8 + j) & 8191] >> 3) & 3);   // lane-private bank, 4 distinct rows
 		else w = (lane & 3) * 1296 * 4 / 4 + (lane >> 2) + 64 * j;  // 4 slices x 8 distinct
 		a[j] = base + 4 * w;
 	}
@@ -59,6 +61,11 @@ int main() {
 		run<1, 1>("red +v (ATOMS.ADD), 32 distinct banks", out, idx, cyc, threads);
 		run<1, 2>("red +v (ATOMS.ADD), random", out, idx, cyc, threads);
 		run<1, 3>("red +v (ATOMS.ADD), 8 addr x 4 lanes", out, idx, cyc, threads);
+		run<0, 5>("red +1 (POPC.INC), lane = bank, random rows", out, idx, cyc, threads);
+		run<0, 6>("red +1 (POPC.INC), lane = bank, 4 rows", out, idx, cyc, threads);
+		run<1, 5>("red +v (ATOMS.ADD), lane = bank, random rows", out, idx, cyc, threads);
+		run<3, 5>("STS, lane = bank, random rows", out, idx, cyc, threads);
+		run<4, 5>("LDS, lane = bank, random rows", out, idx, cyc, threads);
 		run<2, 1>("atom +1 returning, 32 distinct banks", out, idx, cyc, threads);
 		run<3, 1>("STS, 32 distinct banks", out, idx, cyc, threads);
 		run<3, 2>("STS, random", out, idx, cyc, threads);
