@@ -286,7 +286,8 @@ def run_native(args):
     dom = max(share, key=share.get)                # dominant kernel = largest share of the step
     dur_ms, alg_bytes = kern[dom]
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
-    names = {"kmeans_assign": "qvz_kmeans_assign_kernel", "cond_counts": "qvz_cond_counts_kernel",
+    # one cluster and Q <= 41 (this workload): the counting pass is the lane-private byte-plane kernel
+    names = {"kmeans_assign": "qvz_kmeans_assign_kernel", "cond_counts": "qvz_cond_counts_planes_kernel" if k == 1 else "qvz_cond_counts_kernel",
              "quantize_walk": "qvz_quantize_batched_kernel"}
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": ncu_traffic(dom, cfg),
@@ -327,7 +328,7 @@ def ncu_traffic(kernel, cfg):
     if not files:
         return None
     per = json.load(open(files[-1]))["dram_bytes_per_launch"]
-    pick = {"quantize_walk": ("qvz_quantize_batched_kernel",), "cond_counts": ("qvz_cond_counts_kernel",),
+    pick = {"quantize_walk": ("qvz_quantize_batched_kernel",), "cond_counts": ("qvz_cond_counts_kernel", "qvz_cond_counts_planes_kernel"),
             "kmeans_assign": ("qvz_kmeans_assign_kernel",)}[kernel]
     tot = sum(v for k, v in per.items() if any(p in k for p in pick))
     return int(tot) if tot else None

@@ -454,7 +454,8 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 }
 
 // S = columns staged per barrier (4, 2 or 1: the largest whose double buffer fits shared memory)
-template <int DMODE, bool WANT_QV, int S>
+// ONEK = one cluster (the reference's default): no per-line table offset
+template <int DMODE, bool WANT_QV, int S, bool ONEK>
 __global__ void __launch_bounds__(QB_THREADS, QB_CTAS)
 qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint32_t *__restrict__ Dw,
                             const uint8_t *__restrict__ cl, const uint8_t *__restrict__ G,
@@ -513,7 +514,7 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			const uint32_t kraw = cl[pbase + j * QB_THREADS];
 			valid[j] = kraw != QVZ_NO_LINE;
 			const uint32_t k = valid[j] ? kraw : 0;      // a slot without a line walks cluster 0's tables on zero data
-			koff[j] = k * A * A4;
+			koff[j] = ONEK ? 0u : k * A * A4;
 			// column 0: previous value 0 (src/qv_compressor.c:89), its ratio is the first byte of the cluster's R rows
 			vprev[j] = ((uint32_t) __ldg(R + (size_t) k * C * 72) - 1u) << 24;
 			erri[j] = 0;
@@ -578,7 +579,7 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 								const int drawt = (int) __byte_perm(dr[j], 0, 0x0444 + (b << 12));
 								const uint32_t base = (drawt > (int) vprev[j]) ? tab + plane : tab;
 								const uint32_t data = __byte_perm(x[j], 0, 0x4440 + b);
-								const uint32_t row = (vprev[j] & 0x7Fu) * A4 + koff[j];
+								const uint32_t row = ONEK ? (vprev[j] & 0x7Fu) * A4 : (vprev[j] & 0x7Fu) * A4 + koff[j];
 								const uint32_t v = lds_u32(base + row + data * 4);
 								outw[j] = __byte_perm(outw[j], v, (0x3210 & ~(0xF << (4 * b))) + (6 << (4 * b)));
 								if (WANT_QV) qvw[j] = __byte_perm(qvw[j], v, (0x3210 & ~(0xF << (4 * b))) + (4 << (4 * b)));
@@ -658,9 +659,9 @@ int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A) {
 	return QVZ_OK;
 }
 
-template <int DMODE, bool WANT_QV, int S>
+template <int DMODE, bool WANT_QV, int S, bool ONEK>
 static void launch_batched(qvz_gpu *h, uint32_t K, uint32_t A) {
-	auto kern = qvz_quantize_batched_kernel<DMODE, WANT_QV, S>;
+	auto kern = qvz_quantize_batched_kernel<DMODE, WANT_QV, S, ONEK>;
 	const size_t smem = batched_smem(K, A, S);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	const uint64_t nbatch = (uint64_t) (h->L.T / QB_LINES) * h->L.Lr;     // T % QB_LINES == 0 (QVZ_RUN_ALIGN)
@@ -672,9 +673,11 @@ static void launch_batched(qvz_gpu *h, uint32_t K, uint32_t A) {
 
 template <int DMODE, bool WANT_QV>
 static void launch_batched_s(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t S) {
-	if (S == 4) launch_batched<DMODE, WANT_QV, 4>(h, K, A);
-	else if (S == 2) launch_batched<DMODE, WANT_QV, 2>(h, K, A);
-	else launch_batched<DMODE, WANT_QV, 1>(h, K, A);
+	if (K == 1 && S == 4) launch_batched<DMODE, WANT_QV, 4, true>(h, K, A);
+	else if (K == 1 && S == 2) launch_batched<DMODE, WANT_QV, 2, true>(h, K, A);
+	else if (S == 4) launch_batched<DMODE, WANT_QV, 4, false>(h, K, A);
+	else if (S == 2) launch_batched<DMODE, WANT_QV, 2, false>(h, K, A);
+	else launch_batched<DMODE, WANT_QV, 1, false>(h, K, A);
 }
 
 int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, int want_qv, int dmode) {

@@ -1,3 +1,2 @@
-./tools/ubench/atoms > gpurun_out/atoms.log 2>&1
-grep -E "lane = bank|32 distinct banks|random" gpurun_out/atoms.log
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench1.json 2> gpurun_out/bench1.err
+python tools/brief.py n1 < gpurun_out/bench1.json || tail -20 gpurun_out/bench1.err
