@@ -355,3 +355,40 @@ def test_beyond_4g_symbols(gpu, oracle):
             assert np.array_equal(o["line_err"], qs["line_err"]), lo
     finally:
         small.close()
+
+
+@pytest.mark.parametrize("n,c", [(40_000, 150), (9_001, 301), (70_000, 23), (3, 2)])
+def test_one_cluster_counting_paths(gpu, oracle, n, c):
+    """K = 1 (the reference's default): the k-means column sums come out of the count table, and the table is counted
+    by the lane-private byte-plane kernel (whole columns per CTA when C >= SM count, pieces of the left-over columns)
+    or by the word-column kernel (alphabets above Q41, or QVZ_COUNTS_WORDS=1).  All of them must give the oracle's
+    centroid, `moved` log and table -- also when the counts are asked for twice, or after new ids were installed."""
+    import os
+    rows = synth_rows(n, c, seed=31 + c).numpy()
+    init = rows[[n // 2], :c]
+    o = oracle.kmeans(rows, c, init, 4.0)
+    want = oracle.cond_counts(rows, c, 1, o["ids"])
+    for env in (None, "QVZ_COUNTS_WORDS"):
+        if env:
+            os.environ[env] = "1"
+        try:
+            _load(gpu, rows, c)
+            r = gpu.kmeans(init, 4.0)
+            assert r["iters"] == o["iters"]
+            for key in ("ids", "means", "counts", "moved"):
+                assert np.array_equal(r[key], o[key]), (env, key)
+            assert np.array_equal(gpu.cond_counts(), want), env          # the table the k-means pass left behind
+            assert np.array_equal(gpu.cond_counts(), want), env
+            gpu.set_clusters(1, np.zeros(n, np.uint8))                   # new ids: counted again
+            assert np.array_equal(gpu.cond_counts(), want), env
+        finally:
+            if env:
+                del os.environ[env]
+    # a wide alphabet (symbols up to 71) cannot use the 32 private copies: same results through the general kernel
+    wide = rows.copy()
+    wide[::7, : c] = np.minimum(wide[::7, : c].astype(np.int32) + 30, 33 + 71).astype(np.uint8)
+    ow = oracle.kmeans(wide, c, wide[[0], :c], 4.0)
+    _load(gpu, wide, c)
+    rw = gpu.kmeans(wide[[0], :c], 4.0)
+    assert np.array_equal(rw["means"], ow["means"]) and np.array_equal(rw["moved"], ow["moved"])
+    assert np.array_equal(gpu.cond_counts(), oracle.cond_counts(wide, c, 1, ow["ids"]))
