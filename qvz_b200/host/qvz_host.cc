@@ -19,6 +19,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -456,32 +459,39 @@ namespace {
 struct BitWriter {
 	FILE *fp;
 	std::vector<uint8_t> buf;
-	size_t pos = 0;
-	uint32_t cur = 0, nbits = 0;
+	size_t pos = 0, limit;
+	uint64_t acc = 0;                                // bits not yet written, right aligned (always < 8 of them between calls)
+	uint32_t nacc = 0;
 	uint64_t written = 0;
 	bool ok = true;
-	explicit BitWriter(FILE *f) : fp(f), buf((size_t) 1 << 22) {}
+	explicit BitWriter(FILE *f) : fp(f), buf((size_t) 1 << 22), limit(buf.size() - 16) {}
 	void flush() {
 		if (pos && fwrite(buf.data(), 1, pos, fp) != pos) ok = false;
 		written += pos;
 		pos = 0;
 	}
-	inline void put_byte(uint8_t b) {
-		buf[pos++] = b;
-		if (pos == buf.size()) flush();
+	// n <= 32 bits of v, most significant first (stream_write_bits, one bit at a time there).  The whole bytes among the
+	// pending bits are stored with one unconditional 8-byte big-endian store; only the position advances by their count.
+	inline void bits(uint32_t v, uint32_t n) {
+		acc = (acc << n) | v;
+		nacc += n;                                   // <= 7 + 32
+		const uint64_t be = __builtin_bswap64(acc << (64 - nacc));      // nacc == 0: shift by 64 would be undefined
+		if (nacc) memcpy(buf.data() + pos, &be, 8);
+		pos += nacc >> 3;
+		nacc &= 7;
+		acc &= (1ull << nacc) - 1;
+		if (pos >= limit) flush();
 	}
-	inline void bit(uint32_t b) {
-		cur = (cur << 1) | (b & 1);
-		if (++nbits == 8) {
-			put_byte((uint8_t) cur);
-			cur = 0;
-			nbits = 0;
-		}
+	inline void bit(uint32_t b) { bits(b & 1, 1); }
+	inline void run(uint32_t b, uint32_t n) {        // n copies of bit b
+		const uint32_t ones = b ? 0xFFFFFFFFu : 0u;
+		for (; n >= 32; n -= 32) bits(ones, 32);
+		if (n) bits(ones >> (32 - n), n);
 	}
 	void finish() {                                  // stream_finish_byte: pads the byte in progress; on a byte boundary it still emits one zero byte
-		put_byte((uint8_t) (cur << (8 - nbits)));
-		cur = 0;
-		nbits = 0;
+		buf[pos++] = (uint8_t) (acc << (8 - nacc));
+		acc = 0;
+		nacc = 0;
 		flush();
 	}
 };
@@ -499,30 +509,14 @@ struct Coder {
 	int32_t scale3 = 0;
 	BitWriter &os;
 	explicit Coder(BitWriter &w) : os(w) {}
-	inline void step(Stats &s, uint32_t x) {
-		const uint64_t range = (uint64_t) (u - l + 1);
-		uint32_t below = 0;
-		for (uint32_t i = 0; i < x; ++i) below += s.counts[i];
-		const uint32_t upto = below + s.counts[x];
-		u = l + (uint32_t) ((range * upto) / s.n) - 1;
-		l = l + (uint32_t) ((range * below) / s.n);
-		for (;;) {
-			const uint32_t msbL = l >> MSB, msbU = u >> MSB;
-			if (msbL == msbU) {                          // E1/E2: the top bit is decided
-				os.bit(msbL);
-				l = (l & CLEAR) << 1;
-				u = ((u & CLEAR) << 1) + 1;
-				while (scale3 > 0) {
-					os.bit(!msbL);
-					scale3 -= 1;
-				}
-			} else if ((l >> SMSB) == 0x01 && (u >> SMSB) == 0x02) {    // E3: straddling the middle
-				scale3 += 1;
-				u = (((u << 1) & CLEAR) | (1u << MSB)) + 1;
-				l = (l << 1) & CLEAR;
-			} else break;
-		}
-		// update_stats(stats, x, a->r)
+	// cumulative counts of symbol x in model s, then update_stats(stats, x, a->r) (src/qv_stream.c:9-25).  This half of
+	// arithmetic_encoder_step never looks at the interval, so it can run ahead of the coder (qvz_host_encode).
+	static inline void model(Stats &s, uint32_t x, uint32_t &below, uint32_t &upto, uint32_t &n) {
+		uint32_t b = 0;
+		for (uint32_t i = 0; i < x; ++i) b += s.counts[i];
+		below = b;
+		upto = b + s.counts[x];
+		n = s.n;
 		s.counts[x] += STEP;
 		s.n += STEP;
 		if (s.n > R) {
@@ -535,14 +529,51 @@ struct Coder {
 				}
 		}
 	}
+	// the interval half (src/arith.c:38-96)
+	inline void narrow(uint32_t below, uint32_t upto, uint32_t n) {
+		// floor(range*cum / n) without the 64-bit integer divide (the longest latency on the coder's dependency chain):
+		// range*cum < 2^43 and n < 2^21 are exact doubles; v = cum*range * fl(1/n) + 2^-25 is within 2^-29 of t + 2^-25 for
+		// the true quotient t <= 2^22, a non-integer t is at least 1/n >= 2^-21 away from both neighbouring integers and an
+		// integer t lands strictly inside (t, t+1): truncation gives floor(t) in every case.  1/n does not depend on the
+		// interval, so the division itself is off the chain.
+		const uint64_t range = (uint64_t) (u - l + 1);
+		const double inv = 1.0 / (double) n;
+		u = l + (uint32_t) ((double) (range * upto) * inv + 0x1p-25) - 1;
+		l = l + (uint32_t) ((double) (range * below) * inv + 0x1p-25);
+		// The reference rescales one bit per loop turn (src/arith.c:56-96).  A run of E1/E2 turns is the run of leading
+		// bits on which l and u agree: they are emitted together (the pending E3 complements follow the first of them,
+		// as in the reference), then the E3 test is made; identical bits, fewer unpredictable branches.
+		const uint32_t MASK = (1u << M) - 1u;
+		for (;;) {
+			const uint32_t diff = l ^ u;
+			const uint32_t k = diff ? (uint32_t) __builtin_clz(diff << (32 - M)) : M;       // agreeing leading bits of the M-bit bounds
+			if (scale3 > 0 && k) {
+				const uint32_t top = l >> (M - k), first = top >> (k - 1);
+				os.bits(first, 1);
+				os.run(first ^ 1u, (uint32_t) scale3);
+				scale3 = 0;
+				os.bits(top & ((1u << (k - 1)) - 1u), k - 1);
+			} else os.bits(l >> (M - k), k);                                 // k == 0: nothing (l < 2^M)
+			l = (l << k) & MASK;
+			u = ((u << k) & MASK) | ((1u << k) - 1u);
+			if ((l >> SMSB) == 0x01 && (u >> SMSB) == 0x02) {           // E3: straddling the middle
+				scale3 += 1;
+				u = (((u << 1) & CLEAR) | (1u << MSB)) + 1;
+				l = (l << 1) & CLEAR;
+			} else break;
+		}
+	}
+	inline void step(Stats &s, uint32_t x) {
+		uint32_t below, upto, n;
+		model(s, x, below, upto, n);
+		narrow(below, upto, n);
+	}
 	void last() {                                    // encoder_last_step (src/arith.c:99-116)
 		const uint32_t msbL = l >> MSB;
 		os.bit(msbL);
-		while (scale3 > 0) {
-			os.bit(!msbL);
-			scale3 -= 1;
-		}
-		for (int b = (int) MSB - 1; b >= 0; --b) os.bit(l >> b);
+		if (scale3 > 0) os.run(msbL ^ 1u, (uint32_t) scale3);
+		scale3 = 0;
+		os.bits(l & CLEAR, MSB);                     // stream_write_bits(os, a->l, m - 1): the low m-1 bits, most significant first
 		os.finish();
 	}
 };
@@ -591,31 +622,154 @@ extern "C" int qvz_host_encode(const qvz_codebooks *cb, const char *path, uint64
 	BitWriter os(fp);
 	Coder coder(os);
 	int rc = 0;
-	for (uint64_t line = 0; line < n_lines && !rc; ++line) {                // src/qv_compressor.c:76-135 minus the quantization itself
-		const uint32_t k = cluster_ids[line];
-		if (k >= K) {
-			rc = -2;
-			break;
-		}
-		coder.step(cstats, k);                                              // qv_write_cluster (:86)
-		const uint8_t *sym = symbols + line * C;
-		uint32_t prev = 0;
-		for (uint32_t c = 0; c < C; ++c) {
-			const size_t kc = (size_t) k * C + c;
-			const uint32_t ctx = cb->ctx_of[kc * A + prev];                 // choose_quantizer's context lookup (src/codebook.c:163)
-			const uint32_t hi = sym[c] >> 7, state = sym[c] & 0x7Fu;
-			if (ctx == QVZ_CTX_ABSENT) {
+	unsigned nthreads = std::thread::hardware_concurrency();
+	if (nthreads > 8) nthreads = 8;
+	if (n_lines * C < (1u << 20)) nthreads = 1;                             // small inputs: not worth a pipeline
+	if (const char *e = getenv("QVZ_CODER_THREADS")) nthreads = (unsigned) atoi(e);     // explicit: any size (tests)
+	if (nthreads <= 1) {
+		for (uint64_t line = 0; line < n_lines && !rc; ++line) {            // src/qv_compressor.c:76-135 minus the quantization itself
+			const uint32_t k = cluster_ids[line];
+			if (k >= K) {
 				rc = -2;
 				break;
 			}
-			const uint64_t qi = cb->q_off[kc] + 2 * ctx + hi;
-			if (state >= card[qi]) {
-				rc = -2;
-				break;
+			coder.step(cstats, k);                                          // qv_write_cluster (:86)
+			const uint8_t *sym = symbols + line * C;
+			uint32_t prev = 0;
+			for (uint32_t c = 0; c < C; ++c) {
+				const size_t kc = (size_t) k * C + c;
+				const uint32_t ctx = cb->ctx_of[kc * A + prev];             // choose_quantizer's context lookup (src/codebook.c:163)
+				const uint32_t hi = sym[c] >> 7, state = sym[c] & 0x7Fu;
+				if (ctx == QVZ_CTX_ABSENT) {
+					rc = -2;
+					break;
+				}
+				const uint64_t qi = cb->q_off[kc] + 2 * ctx + hi;
+				if (state >= card[qi]) {
+					rc = -2;
+					break;
+				}
+				coder.step(stats[qi], state);                               // compress_qv (:8-11)
+				prev = out_sym[count_off[qi] + state];
 			}
-			coder.step(stats[qi], state);                                   // compress_qv (:8-11)
-			prev = out_sym[count_off[qi] + state];
 		}
+	} else {
+		// The adaptive models are one per (cluster, column, quantizer): what a symbol's model says (cumulative counts, total)
+		// depends on the earlier symbols of the SAME column only, never on the coder's interval.  So blocks of lines go
+		// through two parallel passes on worker threads -- (A) per line: which model codes each symbol (the context chain
+		// along the line); (B) per column, lines in order: the model's answer, then its update -- and the main thread only
+		// narrows the interval with the precomputed (below, upto, n) triples, in the reference's symbol order.  Same bits.
+		uint64_t BL = 8192;                                                 // lines per block
+		if (const char *e = getenv("QVZ_CODER_BLOCK")) BL = strtoull(e, nullptr, 10) ? strtoull(e, nullptr, 10) : BL;
+		const uint64_t per_line = (uint64_t) C + 1;                         // the cluster id, then the columns
+		std::vector<uint32_t> qbuf[2];
+		std::vector<uint64_t> trip[2];                                      // below | upto << 21 | n << 42  (all <= R + STEP < 2^21)
+		for (int b = 0; b < 2; ++b) {
+			qbuf[b].resize(BL * C);
+			trip[b].resize(BL * per_line);
+		}
+		const uint64_t nblocks = (n_lines + BL - 1) / BL;
+		std::mutex mu;
+		std::condition_variable cv;
+		uint64_t produced = 0, consumed = 0;                                // blocks; guarded by mu
+		std::atomic<int> bad(0);
+		auto parallel = [&](auto fn) {
+			std::vector<std::thread> th;
+			for (unsigned t = 1; t < nthreads - 1; ++t) th.emplace_back(fn, t, nthreads - 1);
+			fn(0u, nthreads - 1);
+			for (auto &x : th) x.join();
+		};
+		std::thread producer([&]() {
+			for (uint64_t b = 0; b < nblocks; ++b) {
+				{
+					std::unique_lock<std::mutex> lk(mu);
+					cv.wait(lk, [&] { return b < consumed + 2 || bad.load(); });
+				}
+				if (bad.load()) break;
+				const uint64_t l0 = b * BL, nl = std::min(BL, n_lines - l0);
+				uint32_t *qb = qbuf[b & 1].data();
+				uint64_t *tb = trip[b & 1].data();
+				parallel([&](unsigned t, unsigned nt) {                     // (A) lines [la, lb): the model of every symbol
+					const uint64_t la = nl * t / nt, lb = nl * (t + 1) / nt;
+					for (uint64_t i = la; i < lb; ++i) {
+						const uint32_t k = cluster_ids[l0 + i];
+						if (k >= K) {
+							bad.store(1);
+							return;
+						}
+						const uint8_t *sym = symbols + (l0 + i) * C;
+						uint32_t prev = 0;
+						for (uint32_t c = 0; c < C; ++c) {
+							const size_t kc = (size_t) k * C + c;
+							const uint32_t ctx = cb->ctx_of[kc * A + prev];
+							const uint32_t hi = sym[c] >> 7, state = sym[c] & 0x7Fu;
+							if (ctx == QVZ_CTX_ABSENT) {
+								bad.store(1);
+								return;
+							}
+							const uint64_t qi = cb->q_off[kc] + 2 * ctx + hi;
+							if (state >= card[qi]) {
+								bad.store(1);
+								return;
+							}
+							qb[i * C + c] = (uint32_t) qi;
+							prev = out_sym[count_off[qi] + state];
+						}
+					}
+				});
+				if (bad.load()) break;
+				parallel([&](unsigned t, unsigned nt) {                     // (B) columns [ca, cb): every model in line order
+					const uint32_t ca = (uint32_t) ((uint64_t) C * t / nt), cbnd = (uint32_t) ((uint64_t) C * (t + 1) / nt);
+					for (uint64_t i = 0; i < nl; ++i) {
+						uint32_t below, upto, n;
+						if (t == 0) {                                       // the cluster id is coded first (qv_write_cluster)
+							Coder::model(cstats, cluster_ids[l0 + i], below, upto, n);
+							tb[i * per_line] = (uint64_t) below | ((uint64_t) upto << 21) | ((uint64_t) n << 42);
+						}
+						const uint8_t *sym = symbols + (l0 + i) * C;
+						for (uint32_t c = ca; c < cbnd; ++c) {
+							Coder::model(stats[qb[i * C + c]], sym[c] & 0x7Fu, below, upto, n);
+							tb[i * per_line + 1 + c] = (uint64_t) below | ((uint64_t) upto << 21) | ((uint64_t) n << 42);
+						}
+					}
+				});
+				{
+					std::lock_guard<std::mutex> lk(mu);
+					produced = b + 1;
+				}
+				cv.notify_all();
+			}
+			{
+				std::lock_guard<std::mutex> lk(mu);
+				produced = nblocks;                                         // also on error: releases the consumer
+			}
+			cv.notify_all();
+		});
+		for (uint64_t b = 0; b < nblocks; ++b) {
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				cv.wait(lk, [&] { return produced > b; });
+			}
+			if (bad.load()) break;
+			const uint64_t l0 = b * BL, nl = std::min(BL, n_lines - l0);
+			const uint64_t *tb = trip[b & 1].data();
+			for (uint64_t j = 0; j < nl * per_line; ++j) {
+				const uint64_t v = tb[j];
+				coder.narrow((uint32_t) (v & 0x1FFFFFu), (uint32_t) ((v >> 21) & 0x1FFFFFu), (uint32_t) (v >> 42));
+			}
+			{
+				std::lock_guard<std::mutex> lk(mu);
+				consumed = b + 1;
+			}
+			cv.notify_all();
+		}
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			consumed = nblocks + 2;                                         // on error: lets the producer leave its wait
+		}
+		cv.notify_all();
+		producer.join();
+		if (bad.load()) rc = -2;
 	}
 	if (!rc) coder.last();
 	if (stream_bytes_out) *stream_bytes_out = os.written;
@@ -667,7 +821,9 @@ struct Decoder {
 	}
 	inline uint32_t symbol(const Stats &s) const {                           // the search shared by both decoder steps
 		const uint64_t range = (uint64_t) (u - l + 1), gap = (uint64_t) (t - l + 1);
-		const uint32_t sub = (uint32_t) ((gap * s.n - 1) / range);
+		// floor through a double division (exact, see Coder::narrow): numerator < 2^43, quotient < 2^21, and a non-integer
+		// quotient is at least 1/range >= 2^-22 away from the next integer
+		const uint32_t sub = (uint32_t) ((double) (gap * s.n - 1) / (double) range);
 		uint32_t k = 0, cum = 0;
 		while (sub >= cum) cum += s.counts[k++];
 		return k - 1;
@@ -678,8 +834,9 @@ struct Decoder {
 		uint32_t below = 0;
 		for (uint32_t i = 0; i < x; ++i) below += s.counts[i];
 		const uint32_t upto = below + s.counts[x];
-		u = l + (uint32_t) ((range * upto) / s.n) - 1;
-		l = l + (uint32_t) ((range * below) / s.n);
+		const double inv = 1.0 / (double) s.n;                              // as in Coder::narrow
+		u = l + (uint32_t) ((double) (range * upto) * inv + 0x1p-25) - 1;
+		l = l + (uint32_t) ((double) (range * below) * inv + 0x1p-25);
 		for (;;) {
 			if ((l >> MSB) == (u >> MSB)) {
 				l = (l & CLEAR) << 1;

@@ -49,7 +49,19 @@ def test_design_reproduces_reference_tables(golden):
         assert np.array_equal(getattr(cb, name), golden["t_" + name]), name
 
 
-def test_container_bytes_equal_reference_file(golden, tmp_path):
+@pytest.fixture(params=["sequential", "pipelined"])
+def coder_mode(request, monkeypatch):
+    """qvz_host_encode codes small inputs on one thread and large ones through its model/interval pipeline;
+    the tests force either path (and short blocks, so that the small fixtures span many of them)."""
+    if request.param == "pipelined":
+        monkeypatch.setenv("QVZ_CODER_THREADS", "4")
+        monkeypatch.setenv("QVZ_CODER_BLOCK", "97")
+    else:
+        monkeypatch.setenv("QVZ_CODER_THREADS", "1")
+    return request.param
+
+
+def test_container_bytes_equal_reference_file(golden, tmp_path, coder_mode):
     g = golden
     cb = _design(g)
     n = g["rows"].shape[0]
@@ -63,7 +75,7 @@ def test_container_bytes_equal_reference_file(golden, tmp_path):
     assert written == qvz.size - head.size - 128                             # what start_qv_compression returns
 
 
-def test_encode_rejects_malformed_symbols(golden, tmp_path):
+def test_encode_rejects_malformed_symbols(golden, tmp_path, coder_mode):
     g = golden
     cb = _design(g)
     bad = g["symbols"].copy()
@@ -74,7 +86,7 @@ def test_encode_rejects_malformed_symbols(golden, tmp_path):
 
 @pytest.mark.parametrize("n,c,k,mode,ratio,dist", [(3000, 30, 2, MODE_RATIO, 1.0, DIST_MSE), (2000, 25, 1, MODE_FIXED, 3.0, DIST_LORENTZ),
                                                    (2500, 18, 3, MODE_RATIO, 0.0, DIST_MANHATTAN), (1500, 40, 1, MODE_FIXED, 0.5, DIST_MSE)])
-def test_design_and_file_vs_compiled_reference(ref, tmp_path, n, c, k, mode, ratio, dist):
+def test_design_and_file_vs_compiled_reference(ref, tmp_path, n, c, k, mode, ratio, dist, monkeypatch):
     # fresh inputs through the unmodified reference (oracle/_ref): its counts -> my design == its tables;
     # its encode() of the same file == my container from its symbol stream
     rows = synth_rows(n, c, seed=900 + n).numpy()
@@ -91,8 +103,11 @@ def test_design_and_file_vs_compiled_reference(ref, tmp_path, n, c, k, mode, rat
     rows.tofile(src)
     ref.encode_file(src, dst, None, clusters=k, mode=mode, ratio=ratio, distortion=dist)
     mine = str(tmp_path / "mine.qvz")
-    cb.encode(mine, ids, q["symbols"], DEBUG_SEED)
-    assert np.array_equal(np.fromfile(mine, np.uint8), np.fromfile(dst, np.uint8))
+    for threads, block in (("1", "8192"), ("4", "97"), ("2", "1000")):           # one thread, and the model/interval pipeline
+        monkeypatch.setenv("QVZ_CODER_THREADS", threads)
+        monkeypatch.setenv("QVZ_CODER_BLOCK", block)
+        cb.encode(mine, ids, q["symbols"], DEBUG_SEED)
+        assert np.array_equal(np.fromfile(mine, np.uint8), np.fromfile(dst, np.uint8)), threads
 
 
 def test_decode_reproduces_u_dump(golden, tmp_path):
