@@ -797,6 +797,21 @@ struct BitReader {                                   // stream_read_bit (src/os_
 		}
 		return v;
 	}
+	inline uint32_t bits(uint32_t k) {               // the next k <= 24 bits, first one most significant
+		uint32_t v = 0;
+		while (k) {
+			const uint32_t take = k < 8 - bit ? k : 8 - bit;
+			const uint32_t byte = pos < buf.size() ? buf[pos] : 0u;
+			v = (v << take) | ((byte >> (8 - bit - take)) & ((1u << take) - 1u));
+			bit += take;
+			if (bit == 8) {
+				bit = 0;
+				++pos;
+			}
+			k -= take;
+		}
+		return v;
+	}
 };
 
 struct Decoder {
@@ -837,12 +852,16 @@ struct Decoder {
 		const double inv = 1.0 / (double) s.n;                              // as in Coder::narrow
 		u = l + (uint32_t) ((double) (range * upto) * inv + 0x1p-25) - 1;
 		l = l + (uint32_t) ((double) (range * below) * inv + 0x1p-25);
-		for (;;) {
-			if ((l >> MSB) == (u >> MSB)) {
-				l = (l & CLEAR) << 1;
-				u = ((u & CLEAR) << 1) + 1;
-				t = ((t & CLEAR) << 1) + is.next();
-			} else if ((l >> SMSB) == 0x01 && (u >> SMSB) == 0x02) {
+		const uint32_t MASK = (1u << M) - 1u;
+		for (;;) {                                       // a run of E1/E2 turns = the leading bits l and u agree on (see Coder::narrow)
+			const uint32_t diff = l ^ u;
+			const uint32_t k = diff ? (uint32_t) __builtin_clz(diff << (32 - M)) : M;
+			if (k) {
+				l = (l << k) & MASK;
+				u = ((u << k) & MASK) | ((1u << k) - 1u);
+				t = ((t << k) & MASK) | is.bits(k);
+			}
+			if ((l >> SMSB) == 0x01 && (u >> SMSB) == 0x02) {
 				l = (l << 1) & CLEAR;
 				u = (((u << 1) & CLEAR) | (1u << MSB)) + 1;
 				t = (((t & CLEAR) << 1) ^ (1u << MSB)) + is.next();
@@ -974,23 +993,45 @@ extern "C" int qvz_host_decode(const char *in_path, const char *out_path, uint64
 	BitReader is;
 	is.buf.assign(file.begin() + pos, file.end());
 
-	// adaptive models, exactly as the encoder sets them up but from the decoder's output alphabets
-	std::vector<std::vector<std::vector<std::vector<uint32_t>>>> cnt(K);
-	std::vector<std::vector<std::vector<Stats>>> st(K);
-	for (uint32_t k = 0; k < K; ++k) {
-		cnt[k].resize(C);
-		st[k].resize(C);
+	// adaptive models, exactly as the encoder sets them up but from the decoder's output alphabets -- and everything the
+	// per-symbol loop touches flattened like in qvz_host_encode (one dependent load per lookup instead of a chain of
+	// vector headers): ctx_flat[kc][prev], ratio_flat[kc][ctx], models qoff[kc] + 2*ctx + hi, out_flat[model][state]
+	const size_t KC = (size_t) K * C;
+	std::vector<uint8_t> ctx_flat(KC * A, 0xFF), ratio_flat(KC * A, 0);
+	std::vector<uint64_t> qoff(KC + 1, 0);
+	for (uint32_t k = 0; k < K; ++k)
 		for (uint32_t c = 0; c < C; ++c) {
-			const size_t nqc = books[k].q[c].size();
-			cnt[k][c].resize(nqc);
-			st[k][c].resize(nqc);
-			for (size_t j = 0; j < nqc; ++j) {
-				const uint32_t card = (uint32_t) books[k].q[c][j].out.sym.size();
-				cnt[k][c][j].assign(card, 1u);
-				st[k][c][j] = Stats{cnt[k][c][j].data(), card, card};
+			const size_t kc = (size_t) k * C + c;
+			const ClusterBook &B = books[k];
+			for (uint32_t v = 0; v < A; ++v) {
+				const uint32_t ctx = B.in[c].idx[v];
+				if (ctx != NOT_FOUND) {
+					ctx_flat[kc * A + v] = (uint8_t) ctx;
+					ratio_flat[kc * A + ctx] = B.qratio[c][ctx];
+				}
 			}
+			qoff[kc + 1] = qoff[kc] + B.q[c].size();
 		}
-	}
+	const uint64_t nq = qoff[KC];
+	std::vector<uint64_t> sym_off(nq + 1, 0);
+	for (uint32_t k = 0; k < K; ++k)
+		for (uint32_t c = 0; c < C; ++c)
+			for (size_t j = 0; j < books[k].q[c].size(); ++j) {
+				const uint64_t qi = qoff[(size_t) k * C + c] + j;
+				sym_off[qi + 1] = books[k].q[c][j].out.sym.size();
+			}
+	for (uint64_t i = 0; i < nq; ++i) sym_off[i + 1] += sym_off[i];
+	std::vector<uint32_t> cnt(sym_off[nq], 1u);
+	std::vector<uint8_t> out_flat(sym_off[nq]);
+	std::vector<Stats> st(nq);
+	for (uint32_t k = 0; k < K; ++k)
+		for (uint32_t c = 0; c < C; ++c)
+			for (size_t j = 0; j < books[k].q[c].size(); ++j) {
+				const uint64_t qi = qoff[(size_t) k * C + c] + j;
+				const uint32_t card = (uint32_t) (sym_off[qi + 1] - sym_off[qi]);
+				st[qi] = Stats{&cnt[sym_off[qi]], card, card};
+				memcpy(&out_flat[sym_off[qi]], books[k].q[c][j].out.sym.data(), card);
+			}
 	std::vector<uint32_t> ccounts(K, 1u);
 	Stats cstats{ccounts.data(), K, K};
 
@@ -1006,16 +1047,16 @@ extern "C" int qvz_host_decode(const char *in_path, const char *out_path, uint64
 			rc = -2;
 			break;
 		}
-		const ClusterBook &B = books[k];
 		uint32_t prev = 0;
 		for (uint32_t c = 0; c < C; ++c) {
-			const uint32_t ctx = B.in[c].idx[prev];                          // choose_quantizer (src/codebook.c:162-171)
-			if (ctx == NOT_FOUND) {
+			const size_t kc = (size_t) k * C + c;
+			const uint32_t ctx = ctx_flat[kc * A + prev];                    // choose_quantizer (src/codebook.c:162-171)
+			if (ctx == 0xFF) {
 				rc = -2;
 				break;
 			}
-			const uint32_t qi = 2 * ctx + (well.draw7() >= B.qratio[c][ctx] ? 1u : 0u);
-			Stats &s = st[k][c][qi];
+			const uint64_t qi = qoff[kc] + 2 * ctx + (well.draw7() >= ratio_flat[kc * A + ctx] ? 1u : 0u);
+			Stats &s = st[qi];
 			uint32_t state;
 			if (ln + 1 == lines && c + 1 == C) state = dec.symbol(s);        // decoder_last_step (src/arith.c:190-205): no more bits are read
 			else state = dec.step(s);
@@ -1023,7 +1064,7 @@ extern "C" int qvz_host_decode(const char *in_path, const char *out_path, uint64
 				rc = -2;
 				break;
 			}
-			prev = B.q[c][qi].out.sym[state];
+			prev = out_flat[sym_off[qi] + state];
 			line[c] = (uint8_t) (prev + 33);
 		}
 		if (!rc && fwrite(line.data(), 1, C + 1, fout) != C + 1) rc = -1;
