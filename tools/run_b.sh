@@ -1,1 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py -k "one_cluster_counting or golden" -x -q 2>&1 | tail -15
+timeout 1200 python -m pytest tests/test_cli_gpu.py -x -q 2>&1 | tail -4
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
