@@ -1,2 +1,4 @@
-timeout 1200 python -m pytest tests/test_cli_gpu.py -x -q 2>&1 | tail -4
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench1.json 2> gpurun_out/bench1.err
+python tools/brief.py n1 < gpurun_out/bench1.json || tail -20 gpurun_out/bench1.err
+python -c "
+import json; d=json.loads(open('gpurun_out/bench1.json').read().strip().splitlines()[-1]); print(d['e2e'])"
