@@ -586,9 +586,12 @@ static int start_draws(qvz_gpu *h, const uint32_t seed[32], bool with_draws) {
 	const qvz_layout &L = h->L;
 	int rc = ensure_buf(h, &h->run_states, &h->rs_cap, (size_t) L.T * 32 * sizeof(uint32_t));
 	// draw words of a run in sequence order, Lr*C/4 rows of T words (quantize.cu); the walk reads up to two rows ahead
-	if (!rc && with_draws) rc = ensure_buf(h, &h->Dw, &h->Dw_cap, ((size_t) L.Lr * L.C / 4 + 2) * L.T * sizeof(uint32_t));
+	const size_t draw_words = (size_t) L.Lr * L.C / 4 * L.T;
+	if (!rc && with_draws) rc = ensure_buf(h, &h->Dw, &h->Dw_cap, (draw_words + 2 * (size_t) L.T) * sizeof(uint32_t));
 	if (rc) return rc;
 	if (h->walk_recorded) QVZ_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->ev_walk_done, 0));   // the last walk still reads Dw
+	// the two spare rows are only ever read into bytes the walk discards; keep them defined
+	if (with_draws) QVZ_CUDA(h, cudaMemsetAsync(h->Dw + draw_words, 0, 2 * (size_t) L.T * sizeof(uint32_t), h->aux_stream));
 	cudaStream_t main_stream = h->stream;
 	h->stream = h->aux_stream;                   // well.cu / quantize.cu launch on h->stream
 	cudaError_t e = cudaEventRecord(h->ev_draws_start, h->aux_stream);

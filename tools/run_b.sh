@@ -1,4 +1,4 @@
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench1.json 2> gpurun_out/bench1.err
-python tools/brief.py n1 < gpurun_out/bench1.json || tail -20 gpurun_out/bench1.err
-python -c "
-import json; d=json.loads(open('gpurun_out/bench1.json').read().strip().splitlines()[-1]); print(d['e2e'])"
+for cfg in cfg3 cfg4 cfg5; do
+timeout 900 python bench.py --config $cfg --lines 8000000 --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_$cfg.json 2> gpurun_out/bench_$cfg.err
+python tools/brief.py $cfg < gpurun_out/bench_$cfg.json || tail -5 gpurun_out/bench_$cfg.err
+done
