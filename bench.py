@@ -333,7 +333,11 @@ def run_native(args):
                 "per_kernel_GBps": {names[kk]: round(b / (d * 1e-3) / 1e9, 1) for kk, (d, b) in kern.items() if d > 0},
                 "per_kernel_ms": {**{names[kk]: round(d, 4) for kk, (d, b) in kern.items()}, "qvz_draws_kernel": round(stage["quantize_draws_ms"], 4)},
                 "quantize_stage_GBps_incl_draw_generator": round((2 * sym_per_rank + n) / (stage["quantize_ms"] * 1e-3) / 1e9, 1),
-                "algorithmic_bytes_per_launch": alg_bytes}
+                "algorithmic_bytes_per_launch": alg_bytes,
+                # the whole step by SURVEY.md section 8d's accounting: (I+3)*N*C + (I+2)*N algorithmic bytes for I k-means iterations
+                "whole_step": {"algorithmic_bytes": (iters + 3) * sym_per_rank + (iters + 2) * n,
+                               "achieved": round(((iters + 3) * sym_per_rank + (iters + 2) * n) / (ms_step * 1e-3) / 1e9, 1),
+                               "frac": round(((iters + 3) * sym_per_rank + (iters + 2) * n) / (ms_step * 1e-3) / 1e9 / peak, 4)}}
 
     cpu = cpu_baseline(cfg, args) if world == 1 and not args.no_cpu else None
 
