@@ -1,4 +1,3 @@
-for cfg in cfg3 cfg4 cfg5; do
-timeout 900 python bench.py --config $cfg --lines 8000000 --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_$cfg.json 2> gpurun_out/bench_$cfg.err
-python tools/brief.py $cfg < gpurun_out/bench_$cfg.json || tail -5 gpurun_out/bench_$cfg.err
-done
+timeout 600 python tools/prof_one.py --lines 4000000 --clusters 5 > gpurun_out/plain5.log 2>&1 || exit 1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'assign|cond_counts|batched|draws' -c 16 -o gpurun_out/prof_r1_k5c -f python tools/prof_one.py --lines 4000000 --clusters 5 > gpurun_out/ncu5.log 2>&1
+tail -2 gpurun_out/ncu5.log
