@@ -1,3 +1,5 @@
-timeout 600 python tools/prof_one.py --lines 4000000 --clusters 5 > gpurun_out/plain5.log 2>&1 || exit 1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'assign|cond_counts|batched|draws' -c 16 -o gpurun_out/prof_r1_k5c -f python tools/prof_one.py --lines 4000000 --clusters 5 > gpurun_out/ncu5.log 2>&1
-tail -2 gpurun_out/ncu5.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench1.json 2> gpurun_out/bench1.err
+python tools/brief.py early < gpurun_out/bench1.json || tail -20 gpurun_out/bench1.err
+QVZ_NO_EARLY_DRAWS=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench1b.json 2> gpurun_out/bench1b.err
+python tools/brief.py noearly < gpurun_out/bench1b.json || tail -20 gpurun_out/bench1b.err
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3
