@@ -1,1 +1,1 @@
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --prefetch 1 2>/dev/null | python tools/brief.py prefetch
+timeout 600 python tools/cli_wall.py 2>&1 | tail -5
