@@ -540,28 +540,29 @@ struct Coder {
 		const double inv = 1.0 / (double) n;
 		u = l + (uint32_t) ((double) (range * upto) * inv + 0x1p-25) - 1;
 		l = l + (uint32_t) ((double) (range * below) * inv + 0x1p-25);
-		// The reference rescales one bit per loop turn (src/arith.c:56-96).  A run of E1/E2 turns is the run of leading
-		// bits on which l and u agree: they are emitted together (the pending E3 complements follow the first of them,
-		// as in the reference), then the E3 test is made; identical bits, fewer unpredictable branches.
+		// The reference rescales one bit per loop turn (src/arith.c:56-96).  Its turns come in two runs, each with a closed
+		// form: first E1/E2 while the top bits of l and u agree -- k turns, k = the number of leading bits they share, which
+		// are emitted together (the pending E3 complements follow the first of them, as in the reference) --, then E3 while
+		// l = 01.. and u = 10.. -- j turns, j = how many bits after the top one have l = 1 and u = 0; each drops that bit.
+		// After an E3 turn the top bits still differ, so no E1/E2 turn can follow: one pass, no loop, the same bits.
 		const uint32_t MASK = (1u << M) - 1u;
-		for (;;) {
-			const uint32_t diff = l ^ u;
-			const uint32_t k = diff ? (uint32_t) __builtin_clz(diff << (32 - M)) : M;       // agreeing leading bits of the M-bit bounds
-			if (scale3 > 0 && k) {
-				const uint32_t top = l >> (M - k), first = top >> (k - 1);
-				os.bits(first, 1);
-				os.run(first ^ 1u, (uint32_t) scale3);
-				scale3 = 0;
-				os.bits(top & ((1u << (k - 1)) - 1u), k - 1);
-			} else os.bits(l >> (M - k), k);                                 // k == 0: nothing (l < 2^M)
-			l = (l << k) & MASK;
-			u = ((u << k) & MASK) | ((1u << k) - 1u);
-			if ((l >> SMSB) == 0x01 && (u >> SMSB) == 0x02) {           // E3: straddling the middle
-				scale3 += 1;
-				u = (((u << 1) & CLEAR) | (1u << MSB)) + 1;
-				l = (l << 1) & CLEAR;
-			} else break;
-		}
+		const uint32_t diff = l ^ u;
+		const uint32_t k = diff ? (uint32_t) __builtin_clz(diff << (32 - M)) : M;
+		if (scale3 > 0 && k) {
+			const uint32_t top = l >> (M - k), first = top >> (k - 1);
+			os.bits(first, 1);
+			os.run(first ^ 1u, (uint32_t) scale3);
+			scale3 = 0;
+			os.bits(top & ((1u << (k - 1)) - 1u), k - 1);
+		} else os.bits(l >> (M - k), k);                                     // k == 0: nothing (l < 2^M)
+		l = (l << k) & MASK;
+		u = ((u << k) & MASK) | ((1u << k) - 1u);
+		// now l = 0..., u = 1...  (k == M, l == u before the shift, leaves l = 0, u = MASK)
+		const uint32_t y = ((l & ~u) << 1) & MASK;                           // bit MSB-i set: i-th bit after the top has l = 1, u = 0
+		const uint32_t j = (uint32_t) __builtin_clz(~(y << (32 - M)) | 1u);  // leading ones of the M-bit window (< M: bit 0 of y is 0)
+		scale3 += (int32_t) j;
+		l = (l << j) & CLEAR;
+		u = ((u << j) & CLEAR) | (1u << MSB) | ((1u << j) - 1u);
 	}
 	inline void step(Stats &s, uint32_t x) {
 		uint32_t below, upto, n;
@@ -754,6 +755,7 @@ extern "C" int qvz_host_encode(const qvz_codebooks *cb, const char *path, uint64
 			const uint64_t l0 = b * BL, nl = std::min(BL, n_lines - l0);
 			const uint64_t *tb = trip[b & 1].data();
 			for (uint64_t j = 0; j < nl * per_line; ++j) {
+				__builtin_prefetch(tb + j + 128);                           // the triples were written by other cores
 				const uint64_t v = tb[j];
 				coder.narrow((uint32_t) (v & 0x1FFFFFu), (uint32_t) ((v >> 21) & 0x1FFFFFu), (uint32_t) (v >> 42));
 			}
@@ -852,20 +854,20 @@ struct Decoder {
 		const double inv = 1.0 / (double) s.n;                              // as in Coder::narrow
 		u = l + (uint32_t) ((double) (range * upto) * inv + 0x1p-25) - 1;
 		l = l + (uint32_t) ((double) (range * below) * inv + 0x1p-25);
-		const uint32_t MASK = (1u << M) - 1u;
-		for (;;) {                                       // a run of E1/E2 turns = the leading bits l and u agree on (see Coder::narrow)
-			const uint32_t diff = l ^ u;
-			const uint32_t k = diff ? (uint32_t) __builtin_clz(diff << (32 - M)) : M;
-			if (k) {
-				l = (l << k) & MASK;
-				u = ((u << k) & MASK) | ((1u << k) - 1u);
-				t = ((t << k) & MASK) | is.bits(k);
-			}
-			if ((l >> SMSB) == 0x01 && (u >> SMSB) == 0x02) {
-				l = (l << 1) & CLEAR;
-				u = (((u << 1) & CLEAR) | (1u << MSB)) + 1;
-				t = (((t & CLEAR) << 1) ^ (1u << MSB)) + is.next();
-			} else break;
+		const uint32_t MASK = (1u << M) - 1u;            // one run of E1/E2 turns, then one run of E3 turns: see Coder::narrow
+		const uint32_t diff = l ^ u;
+		const uint32_t k = diff ? (uint32_t) __builtin_clz(diff << (32 - M)) : M;
+		if (k) {
+			l = (l << k) & MASK;
+			u = ((u << k) & MASK) | ((1u << k) - 1u);
+			t = ((t << k) & MASK) | is.bits(k);
+		}
+		const uint32_t y = ((l & ~u) << 1) & MASK;
+		const uint32_t j = (uint32_t) __builtin_clz(~(y << (32 - M)) | 1u);
+		if (j) {                                         // every E3 turn flips the bit that becomes the top one; only the last flip stays inside
+			l = (l << j) & CLEAR;
+			u = ((u << j) & CLEAR) | (1u << MSB) | ((1u << j) - 1u);
+			t = (((t << j) & MASK) ^ (1u << MSB)) | is.bits(j);
 		}
 		update(s, x);
 		return x;
