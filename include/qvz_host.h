@@ -39,8 +39,10 @@ int qvz_host_distortion(int type, double out[QVZ_ALPHABET * QVZ_ALPHABET]);
 int qvz_host_distortion_file(const char *path, double out[QVZ_ALPHABET * QVZ_ALPHABET]);
 
 /* counts: clusters * (1 + 72*(columns-1)) * 72 uint32 in get_cond_pmf order, as produced by qvz_gpu_cond_counts.
- * mode/target: opts->mode / opts->ratio.  threads: clusters are independent and are designed in parallel
- * (0 = one thread per cluster, capped by the hardware).  Returns NULL on bad arguments. */
+ * mode/target: opts->mode / opts->ratio.  threads: total host threads (0 = all the hardware has): clusters are
+ * independent and are designed in parallel; inside a cluster the columns are sequential but the contexts of a column
+ * are not, and share the threads that are left (<= 8 per cluster).  The tables do not depend on the thread count.
+ * Returns NULL on bad arguments. */
 qvz_codebooks *qvz_host_design(const uint32_t *counts, uint32_t clusters, uint32_t columns, int mode, double target,
                                const double distortion[QVZ_ALPHABET * QVZ_ALPHABET], int threads);
 void qvz_host_free(qvz_codebooks *cb);

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -169,8 +170,76 @@ struct ClusterBook {
 	std::vector<std::vector<uint8_t>> qratio;        // qratio[col][ctx]
 };
 
+// A few persistent worker threads for the loops of design_cluster whose iterations are independent (every double is still
+// computed by one thread with the reference's own order of operations, so the results do not depend on the thread count).
+class ForkJoin {
+	std::vector<std::thread> th;
+	std::mutex mu;
+	std::condition_variable cv, done_cv;
+	const std::function<void(size_t)> *job = nullptr;
+	size_t n = 0;
+	std::atomic<size_t> next{0};
+	size_t pending = 0;
+	uint64_t gen = 0;
+	bool stop = false;
+	void work() {
+		for (;;) {
+			const size_t i = next.fetch_add(1);
+			if (i >= n) break;
+			(*job)(i);
+		}
+	}
+	void worker() {
+		uint64_t seen = 0;
+		for (;;) {
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				cv.wait(lk, [&] { return stop || gen != seen; });
+				if (stop) return;
+				seen = gen;
+			}
+			work();
+			{
+				std::lock_guard<std::mutex> lk(mu);
+				if (--pending == 0) done_cv.notify_one();
+			}
+		}
+	}
+public:
+	explicit ForkJoin(unsigned threads) {
+		for (unsigned t = 1; t < threads; ++t) th.emplace_back([this] { worker(); });
+	}
+	~ForkJoin() {
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			stop = true;
+		}
+		cv.notify_all();
+		for (auto &t : th) t.join();
+	}
+	void run(size_t count, const std::function<void(size_t)> &fn) {
+		if (th.empty() || count < 2) {
+			for (size_t i = 0; i < count; ++i) fn(i);
+			return;
+		}
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			job = &fn;
+			n = count;
+			next.store(0);
+			pending = th.size();
+			++gen;
+		}
+		cv.notify_all();
+		work();
+		std::unique_lock<std::mutex> lk(mu);
+		done_cv.wait(lk, [&] { return pending == 0; });
+	}
+};
+
 // the marginals of calculate_statistics (src/codebook.c:208-219) + generate_codebooks (:355-468) for one cluster
-void design_cluster(const uint32_t *counts, uint32_t C, int mode, double target, const double *D, ClusterBook &B) {
+void design_cluster(const uint32_t *counts, uint32_t C, int mode, double target, const double *D, ClusterBook &B, unsigned inner_threads) {
+	ForkJoin pool(inner_threads);
 	const size_t rows = 1 + (size_t) A * (C - 1);
 	// pmf_t.pmf of every conditional pmf: counts / total, all zero when the row was never seen (recalculate_pmf, src/pmf.c:219-230)
 	std::vector<double> condp(rows * A, 0.0);
@@ -242,14 +311,15 @@ void design_cluster(const uint32_t *counts, uint32_t C, int mode, double target,
 		} else {                                         // compute_qpmf_list (:291-330)
 			// p_temp(k, j) = sum_x P(Q_{c-2}=j | X_{c-2}=x) * P(X_{c-1}=k | X_{c-2}=x) * P(X_{c-2}=x): independent of idx
 			ptemp.assign((size_t) A * nprev, 0.0);
-			for (uint32_t k = 0; k < A; ++k)
+			pool.run(A, [&](size_t k) {
 				for (size_t j = 0; j < nprev; ++j) {
 					double t = 0;
 					for (uint32_t x = 0; x < A; ++x)
 						t += prev_qpmf[x * nprev + j] * cond(col - 1, x)[k] * marg[(size_t) (col - 2) * A + x];
 					ptemp[k * nprev + j] = t;
 				}
-			for (uint32_t k = 0; k < A; ++k) {
+			});
+			pool.run(A, [&](size_t k) {
 				for (size_t idx = 0; idx < nu; ++idx) {
 					const uint32_t s = U.sym[idx];
 					double acc = 0.0;
@@ -263,11 +333,11 @@ void design_cluster(const uint32_t *counts, uint32_t C, int mode, double target,
 					qpmf[k * nu + idx] = acc;
 				}
 				renormalize(&qpmf[k * nu], nu);
-			}
+			});
 		}
 
 		xpmf.assign(nu * A, 0.0);                        // compute_xpmf_list (:332-349)
-		for (size_t idx = 0; idx < nu; ++idx) {
+		pool.run(nu, [&](size_t idx) {
 			for (uint32_t k = 0; k < A; ++k) {
 				double t = 0.0;
 				for (uint32_t x = 0; x < A; ++x)
@@ -275,14 +345,14 @@ void design_cluster(const uint32_t *counts, uint32_t C, int mode, double target,
 				xpmf[idx * A + k] = t;
 			}
 			renormalize(&xpmf[idx * A], A);
-		}
+		});
 
-		for (size_t j = 0; j < nu; ++j) {                // one quantizer pair per context (:432-446)
+		pool.run(nu, [&](size_t j) {                     // one quantizer pair per context (:432-446), contexts are independent
 			Quantizer lo, hi;
 			const double *p = &xpmf[j * A];
 			const double ratio = optimize_for_entropy(p, D, entropy_target(p), lo, hi);
 			store(col, (uint32_t) j, std::move(lo), std::move(hi), ratio);
-		}
+		});
 		prev_qpmf.swap(qpmf);
 	}
 }
@@ -348,13 +418,18 @@ extern "C" qvz_codebooks *qvz_host_design(const uint32_t *counts, uint32_t clust
 	cb->distortion.assign(distortion, distortion + A * A);
 	cb->books.resize(clusters);
 	const size_t per_cluster = (1 + (size_t) A * (columns - 1)) * A;
-	unsigned nt = threads > 0 ? (unsigned) threads : std::min<unsigned>(clusters, std::max(1u, std::thread::hardware_concurrency()));
+	// clusters are independent (one thread each); inside a cluster the columns are sequential but the contexts of a column
+	// are not: the threads that are left over (<= 8 per cluster) share them
+	const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+	unsigned nt = threads > 0 ? (unsigned) threads : std::min<unsigned>(clusters, hw);
 	nt = std::min<unsigned>(nt, clusters);
+	unsigned inner = threads > 0 ? std::max(1u, (unsigned) threads / nt) : std::max(1u, hw / nt);
+	if (inner > 8) inner = 8;
 	std::vector<std::thread> pool;
 	for (unsigned t = 0; t < nt; ++t)
 		pool.emplace_back([&, t]() {
 			for (uint32_t k = t; k < clusters; k += nt)
-				design_cluster(counts + k * per_cluster, columns, mode, target, cb->distortion.data(), cb->books[k]);
+				design_cluster(counts + k * per_cluster, columns, mode, target, cb->distortion.data(), cb->books[k], inner);
 		});
 	for (auto &th : pool) th.join();
 

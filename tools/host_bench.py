@@ -40,7 +40,7 @@ with tempfile.TemporaryDirectory() as d:
     same_decode = np.array_equal(np.fromfile(d + "/ref.txt", np.uint8), np.fromfile(d + "/my.txt", np.uint8))
 sym = n * c
 print(json.dumps({
-    "input": f"{n} x {c} synthetic lines, -f 1.0 -d M -c 1 (cfg1 shape); one host core each, except qvz_host_encode: its model passes run on up to 7 worker threads, the interval arithmetic on one",
+    "input": f"{n} x {c} synthetic lines, -f 1.0 -d M -c 1 (cfg1 shape), host threads as available: the reference is single-threaded; qvz_host_design shares the contexts of a column over the threads, qvz_host_encode runs its model passes on worker threads (interval arithmetic on one), qvz_host_decode is sequential",
     "codebook_design_s": {"reference_generate_codebooks": round(ref_design, 2), "qvz_host_design": round(my_design, 2), "tables_identical": bool(same_tables)},
     "coder_Msym_per_s": {"reference_encode_minus_design_incl_its_walk": round(sym / max(ref_encode - ref_design, 1e-9) / 1e6, 2),
                          "qvz_host_encode": round(sym / my_coder / 1e6, 2), "file_identical": bool(same_file)},
