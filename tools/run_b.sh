@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests/test_cli_gpu.py -x -q 2>&1 | tail -3
-timeout 300 python tools/cli_wall.py 2>&1 | tail -4
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 200 python -m pytest tests/test_cli_gpu.py -x -q -k "golden" 2>&1 | tail -2
