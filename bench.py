@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- Gsymbols/s of the qvz front end (k-means + conditional counts + quantize walk) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--lines L]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--config cfg4] [--lines L]
 
-One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic
-quality lines:
-  value      whole-job Gsymbols/s with the rows already resident in HBM (device time, CUDA events on the
-             library's stream, max over ranks);
-  e2e        the same metric through the C ABI with HOST buffers: H2D of the rows, the three stage calls
-             with their D2H results (cluster ids, count tables, symbol stream) inside the timed region;
+Workload (default) = BASELINE.json configs[3], the configuration the metric and the north_star targets are quoted
+on: `qvz -f 1.0 -d M -c 5` on 200 M synthetic 150-bp reads.  It fits one B200; under torchrun the SAME 200 M-line
+file is cut into N contiguous shards, one per rank (strong scaling).  --config cfg1|cfg2|cfg3|cfg5 selects the others.
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over the whole file:
+  value      whole-job Gsymbols/s with the rows and the quantizer tables resident in HBM (device time, CUDA
+             events on the library's stream, max over ranks);
+  e2e        the same metric through the C ABI with HOST buffers: H2D of the rows, the three stage calls with
+             their D2H results (cluster ids, count tables, symbol stream) and the table upload inside the timed region;
   roofline   algorithmic bytes / CUDA-event duration of the dominant kernel vs the measured HBM peak;
-  cpu_baseline  the reference algorithm on the host cores on a bounded sample (rank 0, N=1 only).
+  cpu_baseline  the reference algorithm on the host cores on a bounded sample (rank 0, N=1 only);
+  parity_check  a small job (K = 3) run through the very same (sharded) path and compared bit for bit with the CPU
+             oracle on rank 0 before anything is timed.
 --impl reference times the reference's own CPU implementation (oracle/_ref, else the oracle port).
 """
 from __future__ import annotations
 
 import argparse
+import glob
+import hashlib
 import json
 import os
 import subprocess
@@ -37,15 +44,18 @@ def log(*a):
 
 
 # ------------------------------------------------------------------------------------------ workload
-def workload(args, world):
-    """cfg2 of BASELINE.json at N=1 (the largest single-GPU configuration that the metric is quoted on);
-    under torchrun every rank gets the same per-GPU shard size (weak scaling)."""
+def workload(args):
     from qvz_b200.synth import CONFIGS
     cfg = dict(CONFIGS[args.config])
     if args.lines:
-        cfg["lines"] = args.lines
+        cfg["lines"] = args.lines                  # TOTAL lines of the file (dev / parity runs)
     cfg["name"] = args.config
     return cfg
+
+
+def describe(cfg):
+    return (f"{cfg['name']}: qvz {'-f' if cfg['mode'] == 'ratio' else '-r'} {cfg['ratio']} -d {cfg['dist']} -c {cfg['clusters']}"
+            f" on {cfg['lines']} synthetic {cfg['columns']}-column lines")
 
 
 DIST = {"M": 2, "L": 3, "A": 1}        # include/distortion.h:7-9
@@ -119,66 +129,145 @@ def bind_to_gpu_numa_node(gpu_index):
     return 0
 
 
+def _digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return np.frombuffer(h.digest(), dtype=np.int64).copy()
+
+
+def parity_check(h, fe, rank, world, device):
+    """A 200 000-line, K = 3 job through the same path as the timed one (sharded over the ranks, NCCL all-reduces and
+    all), every output compared with the CPU oracle's on rank 0: cluster ids, conditional counts, symbols, `-u` bytes and
+    per-line distortion of each shard.  The oracle is used here as the checker only."""
+    import torch
+    import torch.distributed as dist
+    from qvz_b200 import hostlib
+    from qvz_b200.dist import kmeans_pick_lines, shard_bounds
+    from qvz_b200.synth import synth_rows
+    n, c, k = 200_000, 150, 3
+    rows = synth_rows(n, c, seed=4321).numpy()     # the same bytes on every rank (CPU generator)
+    b = shard_bounds(n, world)
+    lo, hi = b[rank], b[rank + 1]
+    local = np.ascontiguousarray(rows[lo:hi])
+    picks = kmeans_pick_lines(n, k, GLIBC_RAND_SEED1)
+    init = np.ascontiguousarray(rows[picks, :c])
+    seed = np.full(32, 0x55555555, np.uint32)
+    h.load_rows(local, hi - lo, c, c + 1, first_line=lo)
+    if fe:
+        km = fe.kmeans(init, 4.0)
+        counts = fe.cond_counts(want_host=True)
+    else:
+        km = h.kmeans(init, 4.0)
+        counts = h.cond_counts()
+    cb = hostlib.design_codebooks(counts, c, k, hostlib.MODE_RATIO, 0.5, hostlib.DIST_MSE)
+    q = h.quantize(cb.tables, seed, want_qv=True, want_err=True)
+    mine = np.stack([_digest(km["ids"]), _digest(counts), _digest(q["symbols"]), _digest(q["qv"]), _digest(q["line_err"])])
+    if world > 1:
+        t = torch.from_numpy(mine).to(device)
+        allv = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        allv = [x.cpu().numpy() for x in allv]
+    else:
+        allv = [mine]
+    if rank != 0:
+        return None
+    from oracle.bindings import FlatTables, Oracle
+    O = Oracle()
+    o = O.kmeans(rows, c, init, 4.0)
+    ocounts = O.cond_counts(rows, c, k, o["ids"])
+    ot = FlatTables(k, c, cb.nctx, cb.ctx_of, cb.q_off, cb.qratio, cb.qmap, cb.smap, cb.distortion)
+    r = O.quantize(rows, c, o["ids"], ot, seed)
+    bad = []
+    if km["iters"] != o["iters"]:
+        bad.append("iterations")
+    for g in range(world):
+        l0, l1 = b[g], b[g + 1]
+        want = np.stack([_digest(o["ids"][l0:l1]), _digest(ocounts), _digest(r["symbols"][l0:l1]), _digest(r["qv"][l0:l1]),
+                         _digest(r["line_err"][l0:l1])])
+        for name, x, y in zip(("ids", "counts", "symbols", "qv", "line_err"), allv[g], want):
+            if not np.array_equal(x, y):
+                bad.append(f"{name}@rank{g}")
+    return "ok" if not bad else "MISMATCH: " + ",".join(bad)
+
+
 # ------------------------------------------------------------------------------------------ native arm
 def run_native(args):
     import torch
     import torch.distributed as dist
     from qvz_b200 import lib
+    from qvz_b200.dist import ShardedFrontEnd, kmeans_pick_lines, shard_bounds
     from qvz_b200.synth import synth_rows
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
     if world > 1:
         bind_to_gpu_numa_node(local)               # before any pinned allocation: first touch decides the NUMA node
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = workload(args, world)
-    n, c, k = cfg["lines"], cfg["columns"], cfg["clusters"]
-    first_line = rank * n                          # shard `rank` of a world*n-line file (n % 4 == 0)
+        dist.init_process_group("nccl", device_id=device)
+    cfg = workload(args)
+    total, c, k = cfg["lines"], cfg["columns"], cfg["clusters"]
+    bounds = shard_bounds(total, world)            # contiguous shards, inner boundaries on multiples of 4 lines
+    first_line, n = bounds[rank], bounds[rank + 1] - bounds[rank]
     sym_per_rank = n * c
+    total_sym = total * c
 
-    t0 = time.time()
-    rows_d = synth_rows(n, c, seed=1234 + rank, profile=cfg["profile"], device="cuda")
-    rows = torch.empty(rows_d.shape, dtype=torch.uint8, pin_memory=True)
-    rows.copy_(rows_d)
-    torch.cuda.synchronize()
-    del rows_d
-    torch.cuda.empty_cache()
-    rows_np = rows.numpy()
-    log(f"[rank {rank}] synthetic {n}x{c} ready in {time.time()-t0:.1f}s")
-
-    if world > 1:
-        from qvz_b200.dist import ShardedFrontEnd
-        fe = ShardedFrontEnd(local)
-    else:
-        fe = None
+    fe = ShardedFrontEnd(local) if world > 1 else None
     h = fe.h if fe else lib.Handle(local)
 
+    parity = None
+    if not args.no_parity:
+        t0 = time.time()
+        parity = parity_check(h, fe, rank, world, device)
+        if rank == 0:
+            log(f"parity_check: {parity} ({time.time()-t0:.1f}s)")
+            if parity != "ok":
+                print(json.dumps({"metric": METRIC, "parity_check": parity, "error": "results differ from the CPU oracle: not timing"}), flush=True)
+                sys.exit(1)
+
+    # this rank's shard of the file: generated on the GPU chunk by chunk, parked in pinned host memory
+    t0 = time.time()
+    try:
+        rows = torch.empty((n, c + 1), dtype=torch.uint8, pin_memory=True)
+    except RuntimeError as e:                      # the host cannot pin the shard: pageable memory (slower copies, same bytes)
+        log(f"[rank {rank}] pinned allocation of the rows failed ({e}); using pageable memory")
+        rows = torch.empty((n, c + 1), dtype=torch.uint8)
+    piece = 8_000_000
+    for lo in range(0, n, piece):
+        m = min(piece, n - lo)
+        d = synth_rows(m, c, seed=1234, profile=cfg["profile"], device="cuda", first_line=first_line + lo, total_lines=total)
+        rows[lo:lo + m].copy_(d)
+        del d
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    rows_np = rows.numpy()
+    log(f"[rank {rank}] synthetic lines [{first_line}, {first_line + n}) x {c} ready in {time.time()-t0:.1f}s")
+
     # initial centroids: the rows picked by initialize_kmeans_clustering's unseeded rand() stream (src/cluster.c:199-201)
-    from qvz_b200.dist import kmeans_pick_lines
-    total = n * world
     picks = kmeans_pick_lines(total, k, GLIBC_RAND_SEED1)
     if fe:
         init = fe.broadcast_init_means(picks, rows_np, first_line, c)
     else:
         init = np.ascontiguousarray(rows_np[picks, :c])
     seed = np.full(32, 0x55555555, np.uint32)      # the reference's DEBUG seed (src/qv_stream.c:82)
+    thr = cfg.get("threshold", 4.0)
 
-    # resident inputs + tables (outside the timed region)
+    # resident inputs (outside the timed region): the rows, then -- after one pass of stages 1 and 2 and the host
+    # codebook design -- the quantizer tables
     h.load_rows(rows, n, c, c + 1, first_line=first_line)
     if fe:
-        km = fe.kmeans(init, cfg.get("threshold", 4.0), want_ids=False)
+        km = fe.kmeans(init, thr, want_ids=False)
         counts = fe.cond_counts(want_host=True)
     else:
-        km = h.kmeans(init, cfg.get("threshold", 4.0), want_ids=False)
+        km = h.kmeans(init, thr, want_ids=False)
         counts = h.cond_counts()
     tables, tables_kind = make_tables(cfg, counts)
     tstruct = tables.tables                         # struct qvz_flat_tables view of the designed codebooks
-    log(f"[rank {rank}] k-means iterations {km['iters']}, tables: {tables_kind}")
+    h.upload_tables(tstruct)
+    log(f"[rank {rank}] k-means iterations {km['iters']}, cluster sizes {km['counts'].tolist()}, tables: {tables_kind}")
 
-    ids_host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-    sym_host = torch.empty((n, c), dtype=torch.uint8, pin_memory=True)
     stream = torch.cuda.ExternalStream(h.stream)
 
     def barrier():
@@ -191,26 +280,13 @@ def run_native(args):
         if args.prefetch:
             h.prefetch_draws(seed)                 # the draws depend on the seed only: generated under k-means
         if fe:
-            fe.kmeans(init, cfg.get("threshold", 4.0), want_ids=False)
+            fe.kmeans(init, thr, want_ids=False)
             fe.cond_counts(want_host=False)
         else:
-            h.kmeans(init, cfg.get("threshold", 4.0), want_ids=False)
+            h.kmeans(init, thr, want_ids=False)
             h.cond_counts(want=False)
-        h.quantize(tstruct, seed, want_symbols=False)
-        tm = h.timings()
-        if fe:                                     # the stepping calls are timed by the sharded front end
-            tm["kmeans_ms"], tm["kmeans_assign_ms"], tm["kmeans_iters"] = fe.kmeans_ms, fe.kmeans_assign_ms, km["iters"]
-        return tm
-
-    def step_e2e():
-        h.load_rows(rows, n, c, c + 1, first_line=first_line)
-        if fe:
-            fe.kmeans(init, cfg.get("threshold", 4.0), want_ids=True)
-            fe.cond_counts(want_host=True)
-        else:
-            h.kmeans(init, cfg.get("threshold", 4.0), ids_out=ids_host.numpy())
-            h.cond_counts()
-        h.quantize(tstruct, seed, symbols_out=sym_host)
+        h.quantize(None, seed, want_symbols=False)  # tables resident (upload_tables above)
+        return h.timings()
 
     for _ in range(args.warmup):
         step_resident()
@@ -235,52 +311,34 @@ def run_native(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # e2e: host buffers in, host buffers out
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    try:
+        ids_host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        sym_host = torch.empty((n, c), dtype=torch.uint8, pin_memory=True)
+    except RuntimeError as e:
+        log(f"[rank {rank}] pinned allocation of the outputs failed ({e}); using pageable memory")
+        ids_host = torch.empty(n, dtype=torch.uint8)
+        sym_host = torch.empty((n, c), dtype=torch.uint8)
+
+    def step_e2e():
+        h.load_rows(rows, n, c, c + 1, first_line=first_line)
+        if fe:
+            fe.kmeans(init, thr, want_ids=True)
+            fe.cond_counts(want_host=True)
+        else:
+            h.kmeans(init, thr, ids_out=ids_host.numpy())
+            h.cond_counts()
+        h.quantize(tstruct, seed, symbols_out=sym_host)
+
     step_e2e()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         step_e2e()
     barrier()
-    e2e_s = time.perf_counter() - t0
-
-    # Extra information, not the headline: the same calls with TWO jobs in flight on this GPU (two handles, two host
-    # threads; every job still copies its rows in and its symbols out).  One job cannot overlap its own H2D and D2H --
-    # the symbols exist only after the whole file has been counted -- but PCIe is full duplex, so job A's upload hides
-    # behind job B's download.  This is what compressing a list of files looks like.  (Measured on this pool: 29.4 vs
-    # 26.5 Gsymbols/s -- the two directions overlap far less than full duplex would allow; opt-in, --two-jobs.)
-    two_jobs = None
-    if world == 1 and args.two_jobs:
-        import threading
-        h2 = lib.Handle(local)
-        ids2 = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-        sym2 = torch.empty((n, c), dtype=torch.uint8, pin_memory=True)
-
-        upload = threading.Lock()                  # one upload at a time: the jobs fall into upload/download alternation
-
-        def job(hh, ids_buf, sym_buf, reps):
-            for _ in range(reps):
-                with upload:
-                    hh.load_rows(rows, n, c, c + 1, first_line=first_line)
-                hh.kmeans(init, cfg.get("threshold", 4.0), ids_out=ids_buf.numpy())
-                hh.cond_counts()
-                hh.quantize(tstruct, seed, symbols_out=sym_buf)
-
-        job(h2, ids2, sym2, 1)                     # warm the second handle (buffers, jump tables)
-        torch.cuda.synchronize()
-        th = [threading.Thread(target=job, args=(h, ids_host, sym_host, args.steps)),
-              threading.Thread(target=job, args=(h2, ids2, sym2, args.steps))]
-        t0 = time.perf_counter()
-        for x in th:
-            x.start()
-        for x in th:
-            x.join()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        same = bool(torch.equal(sym_host, sym2))
-        two_jobs = {"value": round(2 * args.steps * sym_per_rank / dt / 1e9, 4), "unit": UNIT, "jobs_in_flight": 2,
-                    "ms_per_job": round(dt / (2 * args.steps) * 1e3, 2), "outputs_identical": same}
-        h2.close()
-    h2d = n * (c + 1) + int(np.asarray(tables.qmap).size * 4)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    table_bytes = int(np.asarray(tables.qmap).size) * 2 + int(np.asarray(tables.ctx_of).size) + 72 * 72 * 8
+    h2d = n * (c + 1) + table_bytes
     d2h = n * c + n + (counts.nbytes if counts is not None else 0)
 
     if world > 1:
@@ -295,9 +353,8 @@ def run_native(args):
     ms_step = ms_total / args.steps
     for key in stage:
         stage[key] /= args.steps
-    total_sym = sym_per_rank * world
     value = total_sym / (ms_step * 1e-3) / 1e9
-    e2e_value = total_sym / (e2e_s / args.steps) / 1e9
+    e2e_value = total_sym / e2e_s / 1e9
 
     peaks = {}
     try:
@@ -305,9 +362,9 @@ def run_native(args):
     except OSError:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    # per-kernel durations (CUDA events on the library's streams, averaged over the timed steps) and algorithmic bytes
-    # (1 B per QV read, 1 B per cluster id, 1 B per emitted symbol; the WELL draws are an
-    # intermediate, not algorithmic I/O -- the draw generator's time is shown but it has no roofline of its own)
+    # per-kernel durations (CUDA events on the library's streams, averaged over the timed steps, rank 0's shard) and
+    # algorithmic bytes (1 B per QV read, 1 B per cluster id, 1 B per emitted symbol; the WELL
+    # draws are an intermediate, not algorithmic I/O -- the draw generator's time is shown but has no roofline of its own)
     walk_ms = stage["quantize_ms"] - stage["quantize_draws_ms"]
     if k == 1:
         # one cluster: the k-means stage IS the counting pass (its column sums are marginals of the count table, csrc/kmeans.cu);
@@ -324,36 +381,39 @@ def run_native(args):
     dom = max(share, key=share.get)                # dominant kernel = largest share of the step
     dur_ms, alg_bytes = kern[dom]
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
-    # one cluster and Q <= 41 (this workload): the counting pass is the lane-private byte-plane kernel
+    # one cluster and Q <= 41: the counting pass is the lane-private byte-plane kernel
     names = {"kmeans_assign": "qvz_kmeans_assign_kernel", "cond_counts": "qvz_cond_counts_planes_kernel" if k == 1 else "qvz_cond_counts_kernel",
              "quantize_walk": "qvz_quantize_batched_kernel"}
+    step_bytes = (iters + 3) * sym_per_rank + (iters + 2) * n      # (I+3) N C + (I+2) N for I k-means iterations
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": ncu_traffic(dom, cfg),
+                "frac": round(achieved / peak, 4), "traffic": ncu_traffic(names[dom], cfg, sym_per_rank),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "per_kernel_GBps": {names[kk]: round(b / (d * 1e-3) / 1e9, 1) for kk, (d, b) in kern.items() if d > 0},
+                "per_kernel_frac": {names[kk]: round(b / (d * 1e-3) / 1e9 / peak, 4) for kk, (d, b) in kern.items() if d > 0},
                 "per_kernel_ms": {**{names[kk]: round(d, 4) for kk, (d, b) in kern.items()}, "qvz_draws_kernel": round(stage["quantize_draws_ms"], 4)},
                 "quantize_stage_GBps_incl_draw_generator": round((2 * sym_per_rank + n) / (stage["quantize_ms"] * 1e-3) / 1e9, 1),
                 "algorithmic_bytes_per_launch": alg_bytes,
-                # the whole step by SURVEY.md section 8d's accounting: (I+3)*N*C + (I+2)*N algorithmic bytes for I k-means iterations
-                "whole_step": {"algorithmic_bytes": (iters + 3) * sym_per_rank + (iters + 2) * n,
-                               "achieved": round(((iters + 3) * sym_per_rank + (iters + 2) * n) / (ms_step * 1e-3) / 1e9, 1),
-                               "frac": round(((iters + 3) * sym_per_rank + (iters + 2) * n) / (ms_step * 1e-3) / 1e9 / peak, 4)}}
+                "whole_step": {"algorithmic_bytes_per_gpu": step_bytes,
+                               "achieved": round(step_bytes / (ms_step * 1e-3) / 1e9, 1),
+                               "frac": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4),
+                               "stage_sum_ms": round(stage["kmeans_ms"] + stage["cond_counts_ms"] + stage["quantize_setup_ms"]
+                                                     + walk_ms, 4)}}
 
     cpu = cpu_baseline(cfg, args) if world == 1 and not args.no_cpu else None
 
     out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": f"{cfg['name']}: {n} lines x {c} columns per GPU, {k} cluster(s), "
-                                  f"{'-f' if cfg['mode']=='ratio' else '-r'} {cfg['ratio']} -d {cfg['dist']}",
-                      "lines_per_gpu": n, "columns": c, "clusters": k, "kmeans_iterations": iters,
-                      "tables": tables_kind, "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2" % (n * c / 1e9),
+           "config": {"workload": describe(cfg) + (f", cut into {world} contiguous shards of {n} lines" if world > 1 else ", one GPU"),
+                      "lines_total": total, "lines_per_gpu": n, "columns": c, "clusters": k, "kmeans_iterations": iters,
+                      "tables": tables_kind, "resident": "rows and quantizer tables in HBM; WELL jump-ahead and draw generation inside the step",
+                      "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2" % (n * c / 1e9),
                       "sharding": "contiguous line shards, NCCL all-reduce of int64 centroid sums and uint32 counts" if world > 1 else "single GPU"},
            "stage_ms": {kk: round(v, 4) for kk, v in stage.items()},
            "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "ms_per_step": round(e2e_s / args.steps * 1e3, 2),
-                   **({"two_jobs_in_flight": two_jobs} if two_jobs else {})},
-           "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
+                   "ms_per_step": round(e2e_s * 1e3, 2), "steps": e2e_steps,
+                   "pinned": bool(rows.is_pinned() and sym_host.is_pinned())},
+           "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "parity_check": parity}
     if cpu:
         out["cpu_baseline"] = cpu
     print(json.dumps(out), flush=True)
@@ -361,20 +421,19 @@ def run_native(args):
         dist.destroy_process_group()
 
 
-def ncu_traffic(kernel, cfg):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-    capture of this very workload (profiles/*_ncu_full_cfg2.json); None when the workload is not the captured one."""
-    import glob
-    if (cfg["name"], cfg["lines"], cfg["columns"], cfg["clusters"]) != ("cfg2", 20_000_000, 150, 1):
-        return None
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full_cfg2.json")))
+def ncu_traffic(kernel, cfg, symbols):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel.  From the committed `ncu --set full`
+    capture of this workload's shape (profiles/*_ncu_full_<config>.json: bytes per symbol of a smaller shard, same columns /
+    clusters / tables) scaled to this launch's symbols; None when there is no capture for the config."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_ncu_full_{cfg['name']}.json")))
     if not files:
         return None
-    per = json.load(open(files[-1]))["dram_bytes_per_launch"]
-    pick = {"quantize_walk": ("qvz_quantize_batched_kernel",), "cond_counts": ("qvz_cond_counts_kernel", "qvz_cond_counts_planes_kernel"),
-            "kmeans_assign": ("qvz_kmeans_assign_kernel",)}[kernel]
-    tot = sum(v for k, v in per.items() if any(p in k for p in pick))
-    return int(tot) if tot else None
+    rec = json.load(open(files[-1]))
+    per = rec.get("dram_bytes_per_symbol", {})
+    for name, v in per.items():
+        if kernel in name:
+            return int(v * symbols)
+    return None
 
 
 # ------------------------------------------------------------------------------------------ CPU legs
@@ -391,6 +450,10 @@ def _cpu_sample(cfg, lines):
     return synth_rows(lines, cfg["columns"], seed=1234, profile=cfg["profile"], device=dev).cpu().numpy()
 
 
+def _sample_picks(lines, k):
+    return [(i * 104_729 + 930_886) % lines for i in range(k)]
+
+
 def cpu_baseline(cfg, args):
     """Reference algorithm on the host: the oracle port's three stages on a bounded sample."""
     from oracle.bindings import Oracle
@@ -398,7 +461,7 @@ def cpu_baseline(cfg, args):
     c, k = cfg["columns"], cfg["clusters"]
     rows = _cpu_sample(cfg, lines)
     O = Oracle()
-    init = rows[[(i * 104_729 + 930_886) % lines for i in range(k)], :c]
+    init = rows[_sample_picks(lines, k), :c]
     seed = np.full(32, 0x55555555, np.uint32)
     t0 = time.perf_counter()
     km = O.kmeans(rows, c, init, cfg.get("threshold", 4.0))
@@ -411,24 +474,26 @@ def cpu_baseline(cfg, args):
     t3 = time.perf_counter()
     t3 -= t2b - t2
     return {"value": round(lines * c / (t3 - t0) / 1e9, 5), "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"first {lines} lines of the workload ({t3-t0:.1f} s: kmeans {t1-t0:.2f} counts {t2-t1:.2f} quantize {t3-t2:.2f})"}
+            "sample": f"first {lines} lines of the workload ({t3-t0:.1f} s: kmeans {t1-t0:.2f} ({km['iters']} iterations) counts {t2-t1:.2f} quantize {t3-t2:.2f})"}
 
 
 def run_reference(args):
     """The reference's own single-threaded C on the host cores: unmodified do_kmeans loop functions,
-    calculate_statistics and the choose_quantizer walk from oracle/_ref/libqvzref.so."""
+    calculate_statistics and the choose_quantizer walk from oracle/_ref/libqvzref.so, on a bounded sample of the workload.
+    generate_codebooks (outside the metric on both arms) runs on another core while stages 1 and 2 are being timed."""
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
     from oracle.bindings import MODE_FIXED, MODE_RATIO, Oracle, Ref, ref_available
-    cfg = workload(args, world)
-    lines = min(cfg["lines"], args.cpu_lines)
+    cfg = workload(args)
     c, k = cfg["columns"], cfg["clusters"]
+    lines = min(cfg["lines"], args.ref_lines if args.ref_lines else (args.cpu_lines if k == 1 else 100_000))
     rows = _cpu_sample(cfg, lines)
-    picks = [(i * 104_729 + 930_886) % lines for i in range(k)]
+    picks = _sample_picks(lines, k)
     seed = np.full(32, 0x55555555, np.uint32)
-    times = []
+    reps = args.warmup + args.steps
+    t_a, t_b = [], []
     if ref_available():
         R = Ref()
         kind = "reference"
@@ -436,19 +501,28 @@ def run_reference(args):
         mk = lambda: R.session(rows, c, k, threshold=cfg.get("threshold", 4.0), mode=mode, ratio=cfg["ratio"], distortion=DIST[cfg["dist"]])
         s0 = mk()
         s0.kmeans(picks)
-        t0 = time.perf_counter()
-        s0.tables()                                  # generate_codebooks: outside the metric (host codebook design)
-        log(f"reference codebook design took {time.perf_counter()-t0:.1f}s (not part of the metric)")
-        for i in range(args.warmup + args.steps):
+        s0.stats()
+        design = {}
+
+        def do_design():
+            t0 = time.perf_counter()
+            s0.tables()                              # generate_codebooks: outside the metric (host codebook design)
+            design["s"] = time.perf_counter() - t0
+
+        th = threading.Thread(target=do_design)
+        th.start()
+        for i in range(reps):                        # stages 1 + 2 on fresh sessions
             s = mk()
             t0 = time.perf_counter()
             s.kmeans(picks)
             s.stats()
-            t1 = time.perf_counter()
+            t_a.append(time.perf_counter() - t0)
+        th.join()
+        log(f"reference codebook design took {design['s']:.1f}s (not part of the metric; ran beside the timed stages 1-2 on another core)")
+        for i in range(reps):                        # stage 3 with the designed tables
+            t0 = time.perf_counter()
             s0.quantize(seed, want_qv=False, want_err=True)
-            t2 = time.perf_counter()
-            if i >= args.warmup:
-                times.append(t2 - t0)
+            t_b.append(time.perf_counter() - t0)
     else:
         O = Oracle()
         kind = "port"
@@ -456,22 +530,23 @@ def run_reference(args):
         km = O.kmeans(rows, c, init, cfg.get("threshold", 4.0))
         tables, _ = make_tables(cfg, O.cond_counts(rows, c, k, km["ids"]))
         otab = _oracle_tables(tables)
-        for i in range(args.warmup + args.steps):
+        for i in range(reps):
             t0 = time.perf_counter()
             km = O.kmeans(rows, c, init, cfg.get("threshold", 4.0))
             O.cond_counts(rows, c, k, km["ids"])
+            t_a.append(time.perf_counter() - t0)
+            t0 = time.perf_counter()
             O.quantize(rows, c, km["ids"], otab, seed, want_qv=False, want_err=True)
-            if i >= args.warmup:
-                times.append(time.perf_counter() - t0)
-    sec = float(np.mean(times))
+            t_b.append(time.perf_counter() - t0)
+    sec = float(np.mean(t_a[args.warmup:]) + np.mean(t_b[args.warmup:]))
     value = lines * c / sec / 1e9
-    sample = f"{lines} lines x {c} columns per step (bounded sample of {cfg['name']}), single thread: the reference has no threading"
+    sample = (f"{lines} lines x {c} columns per step (bounded sample of {cfg['name']}: first lines of the same generator, same flags), "
+              f"single thread: the reference has no threading")
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": f"{cfg['name']}: {cfg['lines']} lines x {c} columns per GPU, {k} cluster(s), "
-                                  f"{'-f' if cfg['mode']=='ratio' else '-r'} {cfg['ratio']} -d {cfg['dist']}",
-                      "lines_per_gpu": cfg["lines"], "columns": c, "clusters": k,
+           "config": {"workload": describe(cfg) + f"; timed on a {lines}-line sample per step", "lines_total": cfg["lines"],
+                      "lines_per_step": lines, "columns": c, "clusters": k,
                       "tables": "the reference's own generate_codebooks on the sample", "sharding": "single host thread"},
            "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
            "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -484,11 +559,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--config", default="cfg2")
-    ap.add_argument("--lines", type=int, default=0, help="override lines per GPU (parity/dev runs)")
-    ap.add_argument("--cpu-lines", type=int, default=1_000_000, help="lines in the bounded CPU sample")
+    ap.add_argument("--config", default="cfg4")
+    ap.add_argument("--lines", type=int, default=0, help="override the TOTAL number of lines (parity/dev runs)")
+    ap.add_argument("--cpu-lines", type=int, default=1_000_000, help="lines in the bounded CPU sample (cpu_baseline)")
+    ap.add_argument("--ref-lines", type=int, default=0, help="lines per step of --impl reference (default: cpu-lines for one cluster, else 100000: the reference needs ~6 min for the K = 5 codebooks alone)")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="timed steps of the host-buffer leg (each moves the whole file twice over PCIe)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--two-jobs", action="store_true", help="also measure e2e with two jobs in flight on the GPU (extra information)")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--prefetch", type=int, default=0, help="1: start the WELL draw generation at the start of the step (overlaps k-means)")
     args = ap.parse_args()
     if args.impl == "reference":

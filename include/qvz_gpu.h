@@ -33,6 +33,7 @@ extern "C" {
 #define QVZ_ALPHABET 72u            /* ALPHABET_SIZE, src/main.c:13; ALPHABET_INDEX_SIZE_HINT, include/pmf.h:11 */
 #define QVZ_MAX_COLUMNS 1022u       /* MAX_READS_PER_LINE, include/lines.h:13 */
 #define QVZ_MAX_KMEANS_ITER 1000u   /* MAX_KMEANS_ITERATIONS, include/cluster.h:9 */
+#define QVZ_MAX_CLUSTERS 255u       /* line_t.cluster and qv_options_t.clusters are uint8_t (include/lines.h:26, include/codebook.h:31) */
 #define QVZ_CTX_ABSENT 0xFFu        /* ALPHABET_SYMBOL_NOT_FOUND (include/pmf.h:9) narrowed to a byte */
 
 /* status codes */
@@ -114,6 +115,15 @@ int qvz_gpu_kmeans_assign_dev(qvz_gpu *h, int64_t *sums_dev);
 int qvz_gpu_kmeans_update_dev(qvz_gpu *h, const int64_t *sums_dev, double *moved_out /* K */,
                               uint32_t *counts_out /* K or NULL */);
 int qvz_gpu_kmeans_end(qvz_gpu *h, uint8_t *cluster_ids_out, uint8_t *means_out);
+/* The same loop without a host wait per iteration: update_async recentres AND evaluates the loop condition of
+ * do_kmeans_clustering (moved > threshold, iteration < max_iter; src/cluster.c:221-234) on the device.  The caller
+ * enqueues iteration i+1 (assign_dev, all-reduce, update_async) before it polls the outcome of iteration i: kernels
+ * enqueued after the run has ended return at once.  poll(idx) waits for the idx-th update_async of the run (at most 3
+ * later ones may be in flight); result() hands out the iteration count, the "Cluster %d moved %f." values
+ * (iters x K doubles, src/cluster.c:127) and cluster_t.count, and reports an empty cluster. */
+int qvz_gpu_kmeans_update_async(qvz_gpu *h, const int64_t *sums_dev, double threshold, uint32_t max_iter);
+int qvz_gpu_kmeans_poll(qvz_gpu *h, uint32_t idx, int *done, uint32_t *iters);
+int qvz_gpu_kmeans_result(qvz_gpu *h, uint32_t *iters_out, double *moved_log_out, uint32_t *counts_out);
 /* the same two steps with the sums crossing to HOST memory, for a single process that drives several devices
  * and adds the (<= 6 KB of) integer sums itself: assign_host copies this shard's sums out, update_host takes the
  * totals of all shards back in and recentres. */
@@ -141,6 +151,10 @@ uint64_t qvz_gpu_cond_counts_len(uint32_t K, uint32_t columns);   /* number of u
  *   caller adds them in line order and divides by the line count to get *dis. */
 int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, const uint32_t well_seed[32],
                      uint8_t *symbols_out, uint8_t *qv_out, double *line_err_out);
+/* The tables of `t` -> device memory, once; qvz_gpu_quantize(h, NULL, ...) then walks with them (they are an INPUT of
+ * stage 3 -- qlist in the reference, src/qv_compressor.c:84 -- so a caller that quantizes the same rows again, or a
+ * measurement of the walk with resident inputs, need not upload them per call).  Valid until the next load_rows. */
+int qvz_gpu_upload_tables(qvz_gpu *h, const struct qvz_flat_tables *t);
 
 /* Optional: start generating the WELL draws for `well_seed` now, on the handle's auxiliary stream.  The draws
  * depend only on the seed and on the resident rows' shape, so a caller that knows the seed early (the reference

@@ -162,6 +162,18 @@ static void release_kmeans(qvz_gpu *h) {
 	free_dev(h->moved); h->moved = nullptr;
 	free_dev(h->counts_dev); h->counts_dev = nullptr; h->counts_cached = 0;
 	free_dev(h->k1_sums); h->k1_sums = nullptr; h->k1_cap = 0; h->k1_valid = 0;
+	free_dev(h->km_ctl); h->km_ctl = nullptr;
+	free_dev(h->moved_log); h->moved_log = nullptr; h->moved_log_cap = 0;
+	free_dev(h->last_counts); h->last_counts = nullptr; h->last_counts_cap = 0;
+	if (h->h_ctl) cudaFreeHost(h->h_ctl);
+	h->h_ctl = nullptr;
+	for (int i = 0; i < QVZ_KM_RING; ++i)
+		if (h->ev_iter[i]) { cudaEventDestroy(h->ev_iter[i]); h->ev_iter[i] = nullptr; }
+	if (h->km_ev) {
+		for (cudaEvent_t e : *h->km_ev) cudaEventDestroy(e);
+		delete h->km_ev;
+		h->km_ev = nullptr;
+	}
 	h->means_b_cap = h->means_w_cap = h->means_sq_cap = h->sums_cap = h->moved_cap = h->counts_cap = 0;
 	if (h->h_moved) cudaFreeHost(h->h_moved);
 	if (h->h_counts) cudaFreeHost(h->h_counts);
@@ -212,6 +224,11 @@ extern "C" int qvz_gpu_open(qvz_gpu **out, int device) {
 	QVZ_CUDA(h, cudaEventCreate(&h->ev_jump_done));
 	QVZ_CUDA(h, cudaEventCreateWithFlags(&h->ev_walk_done, cudaEventDisableTiming));
 	for (int i = 0; i < 8; ++i) QVZ_CUDA(h, cudaEventCreate(&h->ev[i]));
+	for (int i = 0; i < 2; ++i) {
+		QVZ_CUDA(h, cudaEventCreate(&h->ev_km[i]));
+		QVZ_CUDA(h, cudaEventCreate(&h->ev_cc[i]));
+	}
+	for (int i = 0; i < 4; ++i) QVZ_CUDA(h, cudaEventCreate(&h->ev_q[i]));
 	for (int b = 0; b < 2; ++b) {
 		QVZ_CUDA(h, cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
 		QVZ_CUDA(h, cudaEventCreateWithFlags(&h->ev_consumed[b], cudaEventDisableTiming));
@@ -246,12 +263,22 @@ extern "C" void qvz_gpu_close(qvz_gpu *h) {
 	free_dev(h->W);
 	free_dev(h->flat);
 	free_dev(h->G);
+	free_dev(h->rowmap);
+	free_dev(h->reach);
+	free_dev(h->start);
+	free_dev(h->support);
 	free_dev(h->R);
 	free_dev(h->D);
 	free_dev(h->flags);
 	if (h->h_flags) cudaFreeHost(h->h_flags);
 	for (int i = 0; i < 8; ++i)
 		if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+	for (int i = 0; i < 2; ++i) {
+		if (h->ev_km[i]) cudaEventDestroy(h->ev_km[i]);
+		if (h->ev_cc[i]) cudaEventDestroy(h->ev_cc[i]);
+	}
+	for (int i = 0; i < 4; ++i)
+		if (h->ev_q[i]) cudaEventDestroy(h->ev_q[i]);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	free(h);
 }
@@ -259,8 +286,36 @@ extern "C" void qvz_gpu_close(qvz_gpu *h) {
 extern "C" const char *qvz_gpu_last_error(const qvz_gpu *h) { return h ? h->err : "null handle"; }
 extern "C" void *qvz_gpu_stream(qvz_gpu *h) { return h ? (void *) h->stream : nullptr; }
 
+// The k-means and counting stages only RECORD events (no host synchronisation inside the stage calls); the
+// milliseconds are worked out here, when somebody asks.
+static int settle_timings(qvz_gpu *h) {
+	if (h->tm_km_pending) {
+		QVZ_CUDA(h, cudaEventSynchronize(h->ev_km[1]));
+		float ms = 0.f, sum = 0.f;
+		cudaEventElapsedTime(&ms, h->ev_km[0], h->ev_km[1]);
+		h->tm.kmeans_ms = ms;
+		for (uint32_t i = 0; h->km_ev && i + 1 < h->km_ev_used; i += 2) {
+			cudaEventElapsedTime(&ms, (*h->km_ev)[i], (*h->km_ev)[i + 1]);
+			sum += ms;
+		}
+		h->tm.kmeans_assign_ms = sum;
+		h->tm_km_pending = 0;
+	}
+	if (h->tm_cc_pending) {
+		QVZ_CUDA(h, cudaEventSynchronize(h->ev_cc[1]));
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, h->ev_cc[0], h->ev_cc[1]);
+		h->tm.cond_counts_ms = ms;
+		h->tm_cc_pending = 0;
+	}
+	return QVZ_OK;
+}
+
 extern "C" int qvz_gpu_get_timings(qvz_gpu *h, struct qvz_gpu_timings *out) {
 	if (!h || !out) return QVZ_ERR_ARG;
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	int rc = settle_timings(h);
+	if (rc) return rc;
 	*out = h->tm;
 	return QVZ_OK;
 }
@@ -289,6 +344,8 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 	h->draws_state = 0;                          // ... and so do prefetched draws
 	h->k1_valid = 0;
 	h->counts_cached = 0;
+	h->support_valid = 0;
+	h->tab_valid = 0;                            // table images are built for the resident rows (alphabet box, reachable rows)
 
 	qvz_layout &L = h->L;
 	L.n_lines = n_lines;
@@ -306,18 +363,8 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 	L.P = (uint64_t) L.T * L.Lr;
 
 	int rc = ensure_buf(h, &h->Xw, &h->Xw_cap, (size_t) L.C4 * L.P * sizeof(uint32_t));
-	if (!rc && !getenv("QVZ_NO_PLANES")) {
-		// second copy as byte planes for the one-cluster counting pass (cond_counts.cu); optional: without it
-		// (no memory left, or switched off) the word-column kernel counts
-		if (ensure_buf(h, &h->Xb, &h->Xb_cap, (size_t) L.C * L.P) != QVZ_OK) {
-			cudaGetLastError();
-			h->Xb = nullptr;
-			h->Xb_cap = 0;
-		}
-	} else if (!rc) {
-		free_dev(h->Xb); h->Xb = nullptr; h->Xb_cap = 0;
-	}
 	if (rc) return rc;
+	h->Xb_valid = 0;                             // the byte planes of the one-cluster counting pass are made on first use (cond_counts.cu)
 	rc = ensure_buf(h, &h->cl, &h->cl_cap, (size_t) L.P);
 	if (rc) return rc;
 	QVZ_CUDA(h, cudaMemsetAsync(h->flags + 5, 0, sizeof(int), h->stream));
@@ -348,7 +395,7 @@ extern "C" int qvz_gpu_load_rows(qvz_gpu *h, const uint8_t *rows, uint64_t n_lin
 extern "C" int qvz_gpu_kmeans_begin(qvz_gpu *h, uint32_t K, const uint8_t *init_means) {
 	if (!h || !init_means) return QVZ_ERR_ARG;
 	if (!h->Xw) QVZ_FAIL(h, QVZ_ERR_ARG, "kmeans: no rows loaded");
-	if (K == 0 || K > QVZ_MAX_K) QVZ_FAIL(h, QVZ_ERR_UNSUPPORTED, "kmeans: 1 <= clusters <= %d supported", QVZ_MAX_K);
+	if (K == 0 || K > QVZ_MAX_CLUSTERS) QVZ_FAIL(h, QVZ_ERR_ARG, "kmeans: 1 <= clusters <= %u (the cluster id is a uint8_t, include/lines.h:26)", QVZ_MAX_CLUSTERS);
 	QVZ_CUDA(h, cudaSetDevice(h->device));
 	const uint32_t C = h->L.C, C4 = h->L.C4;
 	h->km_K = K;
@@ -358,39 +405,114 @@ extern "C" int qvz_gpu_kmeans_begin(qvz_gpu *h, uint32_t K, const uint8_t *init_
 	if (!rc) rc = ensure_buf(h, &h->sums, &h->sums_cap, ((size_t) K * C + K) * sizeof(int64_t));
 	if (!rc) rc = ensure_buf(h, &h->moved, &h->moved_cap, K * sizeof(double));
 	if (!rc) rc = ensure_buf(h, &h->k1_sums, &h->k1_cap, ((size_t) K * C + K) * sizeof(int64_t));   // the run's local running sums
+	if (!rc) rc = ensure_buf(h, &h->moved_log, &h->moved_log_cap, (size_t) QVZ_MAX_KMEANS_ITER * K * sizeof(double));
+	if (!rc) rc = ensure_buf(h, &h->last_counts, &h->last_counts_cap, K * sizeof(int64_t));
 	if (!rc && K == 1)                           // K == 1 takes its column sums from the count table (kmeans.cu)
 		rc = ensure_buf(h, &h->counts_dev, &h->counts_cap, (size_t) qvz_gpu_cond_counts_len(1, C) * sizeof(uint32_t));
 	if (rc) return rc;
 	h->k1_valid = 0;                             // a new run reads the rows again
 	h->counts_cached = 0;
-	if (!h->h_moved) QVZ_CUDA(h, cudaMallocHost(&h->h_moved, QVZ_MAX_K * sizeof(double)));
-	if (!h->h_counts) QVZ_CUDA(h, cudaMallocHost(&h->h_counts, QVZ_MAX_K * sizeof(int64_t)));
+	h->support_valid = 0;                        // the ids are about to change
+	if (!h->h_moved) QVZ_CUDA(h, cudaMallocHost(&h->h_moved, QVZ_MAX_CLUSTERS * sizeof(double)));
+	if (!h->h_counts) QVZ_CUDA(h, cudaMallocHost(&h->h_counts, QVZ_MAX_CLUSTERS * sizeof(int64_t)));
+	if (!h->km_ctl) QVZ_CUDA(h, cudaMalloc(&h->km_ctl, QVZ_CTL_WORDS * sizeof(uint32_t)));
+	if (!h->h_ctl) QVZ_CUDA(h, cudaMallocHost(&h->h_ctl, QVZ_KM_RING * QVZ_CTL_WORDS * sizeof(uint32_t)));
+	for (int i = 0; i < QVZ_KM_RING; ++i)
+		if (!h->ev_iter[i]) QVZ_CUDA(h, cudaEventCreateWithFlags(&h->ev_iter[i], cudaEventDisableTiming));
+	if (!h->km_ev) h->km_ev = new std::vector<cudaEvent_t>();
+	h->km_enq = 0;
+	h->km_ev_used = 0;
+	QVZ_CUDA(h, cudaMemsetAsync(h->km_ctl, 0, QVZ_CTL_WORDS * sizeof(uint32_t), h->stream));
 	QVZ_CUDA(h, cudaMemcpyAsync(h->means_b, init_means, (size_t) K * C, cudaMemcpyHostToDevice, h->stream));
 	h->K = K;
-	return qvz_kmeans_launch_update(h, nullptr);     // pack the initial centroids
+	QVZ_CUDA(h, cudaEventRecord(h->ev_km[0], h->stream));
+	return qvz_kmeans_launch_update(h, nullptr, 0.0, 0);     // pack the initial centroids
 }
 
 extern "C" int qvz_gpu_kmeans_assign_dev(qvz_gpu *h, int64_t *sums_dev) {
 	if (!h || !sums_dev || !h->km_K) return QVZ_ERR_ARG;
 	QVZ_CUDA(h, cudaSetDevice(h->device));
-	return qvz_kmeans_launch_assign(h, sums_dev);
+	std::vector<cudaEvent_t> &pool = *h->km_ev;              // one event pair per assign launch, read in settle_timings
+	while (pool.size() < (size_t) h->km_ev_used + 2) {
+		cudaEvent_t e;
+		QVZ_CUDA(h, cudaEventCreate(&e));
+		pool.push_back(e);
+	}
+	QVZ_CUDA(h, cudaEventRecord(pool[h->km_ev_used], h->stream));
+	int rc = h->km_K > QVZ_MAX_K ? qvz_kmeans_launch_assign_wide(h, sums_dev) : qvz_kmeans_launch_assign(h, sums_dev);
+	if (rc) return rc;
+	QVZ_CUDA(h, cudaEventRecord(pool[h->km_ev_used + 1], h->stream));
+	h->km_ev_used += 2;
+	return QVZ_OK;
 }
 
+// recalculate_means + the loop decision of do_kmeans_clustering (src/cluster.c:221-234) on the device: nothing here
+// waits for the GPU.  The caller may enqueue the NEXT iteration right away (its kernels return at once if this one
+// ended the run) and ask for the outcome later with qvz_gpu_kmeans_poll.
+extern "C" int qvz_gpu_kmeans_update_async(qvz_gpu *h, const int64_t *sums_dev, double threshold, uint32_t max_iter) {
+	if (!h || !sums_dev || !h->km_K) return QVZ_ERR_ARG;
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	int rc = qvz_kmeans_launch_update(h, sums_dev, threshold, max_iter);
+	if (rc) return rc;
+	const uint32_t slot = h->km_enq % QVZ_KM_RING;
+	QVZ_CUDA(h, cudaMemcpyAsync(h->h_ctl + slot * QVZ_CTL_WORDS, h->km_ctl, QVZ_CTL_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+	QVZ_CUDA(h, cudaEventRecord(h->ev_iter[slot], h->stream));
+	QVZ_CUDA(h, cudaEventRecord(h->ev_km[1], h->stream));
+	h->tm_km_pending = 1;
+	h->km_enq += 1;
+	return QVZ_OK;
+}
+
+// outcome of the idx-th update of this run (0-based); at most QVZ_KM_RING - 1 later updates may have been enqueued
+extern "C" int qvz_gpu_kmeans_poll(qvz_gpu *h, uint32_t idx, int *done, uint32_t *iters) {
+	if (!h || !h->km_K || idx >= h->km_enq || h->km_enq - idx > QVZ_KM_RING) return QVZ_ERR_ARG;
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	const uint32_t slot = idx % QVZ_KM_RING;
+	QVZ_CUDA(h, cudaEventSynchronize(h->ev_iter[slot]));
+	if (done) *done = (int) h->h_ctl[slot * QVZ_CTL_WORDS + QVZ_CTL_DONE];
+	if (iters) *iters = h->h_ctl[slot * QVZ_CTL_WORDS + QVZ_CTL_ITER];
+	return QVZ_OK;
+}
+
+// after the run: iteration count, the "Cluster %d moved %f." log (iters x K, at most QVZ_MAX_KMEANS_ITER rows) and cluster_t.count
+extern "C" int qvz_gpu_kmeans_result(qvz_gpu *h, uint32_t *iters_out, double *moved_log_out, uint32_t *counts_out) {
+	if (!h || !h->km_K) return QVZ_ERR_ARG;
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	const uint32_t K = h->km_K;
+	QVZ_CUDA(h, cudaMemcpyAsync(h->h_ctl, h->km_ctl, QVZ_CTL_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->h_counts, h->last_counts, K * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+	int empty = 0;
+	int rc = take_flag(h, 1, &empty);                // synchronises the stream
+	if (rc) return rc;
+	const uint32_t iters = h->h_ctl[QVZ_CTL_ITER];
+	h->tm.kmeans_iters = iters;
+	if (iters_out) *iters_out = iters;
+	if (counts_out)
+		for (uint32_t k = 0; k < K; ++k) counts_out[k] = (uint32_t) h->h_counts[k];
+	if (moved_log_out && iters) {
+		const uint32_t rows = iters < QVZ_MAX_KMEANS_ITER ? iters : QVZ_MAX_KMEANS_ITER;
+		QVZ_CUDA(h, cudaMemcpyAsync(moved_log_out, h->moved_log, (size_t) rows * K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+		QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+	}
+	if (empty) QVZ_FAIL(h, QVZ_ERR_EMPTY_CLUSTER, "kmeans: a cluster has no lines (the reference divides by zero, src/cluster.c:113)");
+	return QVZ_OK;
+}
+
+// blocking form of one recentering: the caller decides whether to go on (kept for callers that add the sums themselves)
 extern "C" int qvz_gpu_kmeans_update_dev(qvz_gpu *h, const int64_t *sums_dev, double *moved_out, uint32_t *counts_out) {
 	if (!h || !sums_dev || !h->km_K) return QVZ_ERR_ARG;
 	QVZ_CUDA(h, cudaSetDevice(h->device));
-	const uint32_t K = h->km_K, C = h->L.C;
-	int rc = qvz_kmeans_launch_update(h, sums_dev);
+	const uint32_t K = h->km_K;
+	int rc = qvz_gpu_kmeans_update_async(h, sums_dev, -1.0, 0xFFFFFFFFu);      // moved >= 0 > -1: never ends the run by itself
 	if (rc) return rc;
-	int64_t *cnt = h->h_counts;
 	QVZ_CUDA(h, cudaMemcpyAsync(h->h_moved, h->moved, K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-	QVZ_CUDA(h, cudaMemcpyAsync(cnt, sums_dev + (size_t) K * C, K * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+	QVZ_CUDA(h, cudaMemcpyAsync(h->h_counts, h->last_counts, K * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
 	int empty = 0;
 	rc = take_flag(h, 1, &empty);                    // synchronises the stream
 	if (rc) return rc;
 	for (uint32_t k = 0; k < K; ++k) {
 		if (moved_out) moved_out[k] = h->h_moved[k];
-		if (counts_out) counts_out[k] = (uint32_t) cnt[k];
+		if (counts_out) counts_out[k] = (uint32_t) h->h_counts[k];
 	}
 	if (empty) QVZ_FAIL(h, QVZ_ERR_EMPTY_CLUSTER, "kmeans: a cluster has no lines (the reference divides by zero, src/cluster.c:113)");
 	return QVZ_OK;
@@ -435,48 +557,50 @@ extern "C" int qvz_gpu_kmeans(qvz_gpu *h, uint32_t K, const uint8_t *init_means,
 {
 	int rc = qvz_gpu_kmeans_begin(h, K, init_means);
 	if (rc) return rc;
-	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
-	std::vector<double> moved(K);
-	uint32_t iter = 0;
-	bool loop = true;
-	float assign_ms = 0.f;
-	// do_kmeans_clustering: while (iter_count < MAX_KMEANS_ITERATIONS && loop)  (src/cluster.c:221)
-	while (iter < max_iter && loop) {
-		QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));
-		rc = qvz_gpu_kmeans_assign_dev(h, h->sums);
+	// do_kmeans_clustering: while (iter_count < MAX_KMEANS_ITERATIONS && loop)  (src/cluster.c:221).  The loop
+	// condition is evaluated on the device (kmeans.cu: update kernel), and iteration i+1 is enqueued BEFORE the
+	// host looks at the outcome of iteration i: if i ended the run, the extra launches return immediately; if
+	// not, the GPU never waited for the host.
+	auto enqueue = [&]() -> int {
+		int r = qvz_gpu_kmeans_assign_dev(h, h->sums);
+		return r ? r : qvz_gpu_kmeans_update_async(h, h->sums, threshold, max_iter);
+	};
+	if (max_iter) {
+		rc = enqueue();
 		if (rc) return rc;
-		QVZ_CUDA(h, cudaEventRecord(h->ev[EV_D], h->stream));
-		rc = qvz_gpu_kmeans_update_dev(h, h->sums, moved.data(), counts_out);
-		if (rc) return rc;
-		assign_ms += ev_ms(h, EV_C, EV_D);
-		double move_max = 0.0;
-		for (uint32_t k = 0; k < K; ++k) {
-			if (moved[k] > move_max) move_max = moved[k];
-			if (moved_log_out) moved_log_out[(size_t) iter * K + k] = moved[k];
+		for (uint32_t i = 0;; ++i) {
+			if (i + 1 < max_iter) {
+				rc = enqueue();
+				if (rc) return rc;
+			}
+			int done = 0;
+			rc = qvz_gpu_kmeans_poll(h, i, &done, nullptr);
+			if (rc) return rc;
+			if (done || i + 1 >= max_iter) break;
 		}
-		loop = move_max > threshold;             // src/cluster.c:231-233
-		iter += 1;
 	}
-	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
-	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
-	h->tm.kmeans_ms = ev_ms(h, EV_A, EV_B);
-	h->tm.kmeans_assign_ms = assign_ms;
-	h->tm.kmeans_iters = iter;
-	if (iters_out) *iters_out = iter;
+	rc = qvz_gpu_kmeans_result(h, iters_out, moved_log_out, counts_out);
+	if (rc) return rc;
 	return qvz_gpu_kmeans_end(h, cluster_ids_out, means_out);
 }
 
 extern "C" int qvz_gpu_set_clusters(qvz_gpu *h, uint32_t K, const uint8_t *cluster_ids) {
 	if (!h || !cluster_ids) return QVZ_ERR_ARG;
 	if (!h->Xw) QVZ_FAIL(h, QVZ_ERR_ARG, "set_clusters: no rows loaded");
-	if (K == 0 || K > 255) QVZ_FAIL(h, QVZ_ERR_ARG, "set_clusters: bad cluster count");
+	if (K == 0 || K > QVZ_MAX_CLUSTERS) QVZ_FAIL(h, QVZ_ERR_ARG, "set_clusters: bad cluster count");
 	QVZ_CUDA(h, cudaSetDevice(h->device));
 	h->counts_cached = 0;
+	h->support_valid = 0;
+	h->k1_valid = 0;                             // running sums of a k-means run in progress no longer match the ids
+	h->K = 0;
 	int rc = pipeline_h2d(h, cluster_ids, 1, 1, [&](const piece &pc) {
-		return qvz_layout_ids_from_lines(h, pc.r0, pc.nr, h->stage[pc.buf]);
+		return qvz_layout_ids_from_lines(h, pc.r0, pc.nr, h->stage[pc.buf], K);
 	});
 	if (rc) return rc;
-	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+	int bad = 0;
+	rc = take_flag(h, 6, &bad);                  // synchronises the stream
+	if (rc) return rc;
+	if (bad) QVZ_FAIL(h, QVZ_ERR_ARG, "set_clusters: a cluster id is >= %u", K);
 	h->K = K;
 	return QVZ_OK;
 }
@@ -486,7 +610,7 @@ extern "C" int qvz_gpu_cond_counts_dev(qvz_gpu *h, uint32_t *counts_dev) {
 	if (!h || !counts_dev) return QVZ_ERR_ARG;
 	if (!h->Xw || !h->K) QVZ_FAIL(h, QVZ_ERR_ARG, "cond_counts: rows and cluster ids must be resident first");
 	QVZ_CUDA(h, cudaSetDevice(h->device));
-	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
+	QVZ_CUDA(h, cudaEventRecord(h->ev_cc[0], h->stream));
 	if (h->counts_cached && h->K == 1) {
 		// the K == 1 k-means pass of these rows already counted them (kmeans.cu): same table, no second pass
 		if (counts_dev != h->counts_dev)
@@ -496,9 +620,12 @@ extern "C" int qvz_gpu_cond_counts_dev(qvz_gpu *h, uint32_t *counts_dev) {
 		int rc = qvz_cond_counts_launch(h, counts_dev);
 		if (rc) return rc;
 	}
-	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
-	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
-	h->tm.cond_counts_ms = ev_ms(h, EV_A, EV_B);
+	QVZ_CUDA(h, cudaEventRecord(h->ev_cc[1], h->stream));
+	{                                            // which values occur where: lets the quantize stage stage reachable table rows only
+		int rc = qvz_cond_counts_support(h, (h->counts_cached && h->K == 1) ? h->counts_dev : counts_dev);
+		if (rc) return rc;
+	}
+	h->tm_cc_pending = 1;                        // no host synchronisation here: the table is ordered on the handle's stream
 	return QVZ_OK;
 }
 
@@ -607,27 +734,108 @@ static int start_draws(qvz_gpu *h, const uint32_t seed[32], bool with_draws) {
 	return QVZ_OK;
 }
 
-// the batched walk is possible for some A >= the lower bound smax + 2 (see qvz_gpu_quantize)
-static bool batched_possible(const qvz_gpu *h, uint32_t clusters) {
+// Could the batched walk be possible?  (decided for good in qvz_gpu_upload_tables; a wrong guess costs an unused draw pass)
+static bool batched_possible(const qvz_gpu *h) {
 	uint32_t A = (h->smax + 2) & ~1u;
-	if (A > 72) A = 72;
-	return !getenv("QVZ_FORCE_LINE_MAJOR") && qvz_quantize_batched_group(clusters, A) > 0;
+	return !getenv("QVZ_FORCE_LINE_MAJOR") && A <= 62;
 }
 
 extern "C" int qvz_gpu_prefetch_draws(qvz_gpu *h, const uint32_t well_seed[32]) {
 	if (!h || !well_seed) return QVZ_ERR_ARG;
 	if (!h->Xw) QVZ_FAIL(h, QVZ_ERR_ARG, "prefetch_draws: no rows loaded");
 	QVZ_CUDA(h, cudaSetDevice(h->device));
-	return start_draws(h, well_seed, batched_possible(h, h->K ? h->K : 1));
+	return start_draws(h, well_seed, h->tab_valid ? h->tab_A != 0 : batched_possible(h));
+}
+
+// The per-column images of the batched walk from the resident W / R (quantize.cu).  use_support: seed the reachability
+// pass with the data values the counting stage saw per (cluster, column); the images then hold exactly the rows these
+// lines can reach.  Synchronises once (the image geometry depends on the tables' content).
+static int build_images(qvz_gpu *h, bool use_support) {
+	const uint32_t K = h->tab_K, C = h->tab_C, A = h->tab_box;
+	uint32_t rows = 0;
+	h->tab_support_used = 0;
+	if (!getenv("QVZ_FORCE_LINE_MAJOR") && A <= 62) {
+		const int compact = !getenv("QVZ_NO_REACH");
+		const uint32_t *support = (use_support && compact && h->support_valid && h->support_K >= K && !getenv("QVZ_NO_SUPPORT")) ? h->support : nullptr;
+		QVZ_CUDA(h, cudaMemsetAsync(h->flags + 7, 0, sizeof(int), h->stream));
+		int rc = qvz_quantize_rows(h, K, C, A, compact, support);
+		if (rc) return rc;
+		QVZ_CUDA(h, cudaMemcpyAsync(h->h_flags, h->flags, QVZ_NFLAGS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+		QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+		rows = 1 + (uint32_t) h->h_flags[7];         // + the poison row
+		if (rows > 256 || qvz_quantize_batched_group(rows, A) == 0) rows = 0;
+		if (rows && support) h->tab_support_used = 1;
+	}
+	if (rows) {
+		int rc = ensure_buf(h, &h->G, &h->G_cap, qvz_quantize_image_bytes(C, rows, A));
+		if (rc) return rc;
+		rc = qvz_quantize_compact(h, K, C, A, rows);
+		if (rc) return rc;
+	}
+	h->tab_A = rows ? A : 0;
+	h->tab_rows = rows;
+	h->tab_dmode = rows ? h->tab_dm : h->tab_toeplitz;
+	return QVZ_OK;
+}
+
+// Tables -> device: the full 72 x 72 composition (W, R), the distortion mode, and -- when they fit -- the per-column
+// images of the batched walk (quantize.cu).  Synchronises once (the image geometry depends on the tables' content).
+extern "C" int qvz_gpu_upload_tables(qvz_gpu *h, const struct qvz_flat_tables *t) {
+	if (!h || !t) return QVZ_ERR_ARG;
+	if (!h->Xw) QVZ_FAIL(h, QVZ_ERR_ARG, "upload_tables: no rows loaded");
+	if (t->columns != h->L.C || t->clusters == 0 || t->clusters > QVZ_MAX_CLUSTERS)
+		QVZ_FAIL(h, QVZ_ERR_ARG, "upload_tables: tables are for %u clusters x %u columns, the rows have %u columns", t->clusters, t->columns, h->L.C);
+	QVZ_CUDA(h, cudaSetDevice(h->device));
+	h->tab_valid = 0;
+	if (h->walk_recorded) QVZ_CUDA(h, cudaEventSynchronize(h->ev_walk_done));       // a previous walk may still read the images
+	int toeplitz = 0;
+	int rc = upload_tables(h, t, &toeplitz);
+	if (rc) return rc;
+	const uint32_t K = t->clusters, C = t->columns, KC = K * C;
+	// distortion mode of the batched walk: 3 = (x-y)^2 (-d M), 4 = |x-y| (-d A), 2 = other integers of |x-y|, 1 = doubles of |x-y| (-d L), 0 = any matrix
+	int dm = toeplitz;
+	if (toeplitz == 2) {
+		bool sq = true, ab = true;
+		for (uint32_t d = 0; d < 72; ++d) {
+			if (t->distortion[d] != (double) (d * d)) sq = false;
+			if (t->distortion[d] != (double) d) ab = false;
+		}
+		dm = sq ? 3 : ab ? 4 : 2;
+	}
+	// A-1 = max(largest symbol in the rows, largest quantized value a present context can emit for such a symbol)
+	QVZ_CUDA(h, cudaMemsetAsync(h->flags + 4, 0, sizeof(int), h->stream));
+	QVZ_CUDA(h, cudaMemsetAsync(h->flags + 7, 0, sizeof(int), h->stream));
+	rc = qvz_quantize_vmax(h, KC, h->smax);
+	if (rc) return rc;
+	rc = ensure_buf(h, &h->rowmap, &h->rowmap_cap, (size_t) KC * 72);
+	if (!rc) rc = ensure_buf(h, &h->reach, &h->reach_cap, (size_t) KC * 72);
+	if (!rc) rc = ensure_buf(h, &h->start, &h->start_cap, (size_t) K * sizeof(uint32_t));
+	if (rc) return rc;
+	QVZ_CUDA(h, cudaMemcpyAsync(h->h_flags, h->flags, QVZ_NFLAGS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
+	if (h->h_flags[3]) {
+		h->h_flags[3] = 0;
+		QVZ_CUDA(h, cudaMemcpyAsync(h->flags + 3, h->h_flags + 3, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+		QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: malformed flat tables (context index or quantized value out of range)");
+	}
+	const uint32_t vmax = (uint32_t) h->h_flags[4] > h->smax ? (uint32_t) h->h_flags[4] : h->smax;
+	h->tab_K = K;
+	h->tab_C = C;
+	h->tab_box = (vmax + 2) & ~1u;               // even, >= vmax + 1
+	h->tab_toeplitz = toeplitz;
+	h->tab_dm = dm;
+	rc = build_images(h, true);
+	if (rc) return rc;
+	h->tab_valid = 1;
+	return QVZ_OK;
 }
 
 extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, const uint32_t well_seed[32],
                                 uint8_t *symbols_out, uint8_t *qv_out, double *line_err_out)
 {
-	if (!h || !t || !well_seed) return QVZ_ERR_ARG;
+	if (!h || !well_seed) return QVZ_ERR_ARG;
 	if (!h->Xw || !h->K) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: rows and cluster ids must be resident first");
-	if (t->columns != h->L.C || t->clusters < h->K)
-		QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: tables are for %u clusters x %u columns, data has %u x %u", t->clusters, t->columns, h->K, h->L.C);
+	if (!t && !h->tab_valid) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: no tables given and none uploaded (qvz_gpu_upload_tables)");
 	QVZ_CUDA(h, cudaSetDevice(h->device));
 	const qvz_layout &L = h->L;
 	const size_t wbytes = (size_t) L.C4 * L.P * sizeof(uint32_t);
@@ -640,49 +848,28 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	// draws first (aux stream), unless a prefetch for this seed is already in flight or done
 	const bool prefetched = h->draws_state && memcmp(h->draws_seed, well_seed, sizeof(h->draws_seed)) == 0;
 	if (!prefetched) {
-		rc = start_draws(h, well_seed, batched_possible(h, t->clusters));
+		rc = start_draws(h, well_seed, t ? batched_possible(h) : h->tab_A != 0);
 		if (rc) return rc;
 	}
-	int toeplitz = 0;
-	rc = upload_tables(h, t, &toeplitz);
-	if (rc) return rc;
+	if (t) {
+		rc = qvz_gpu_upload_tables(h, t);            // (synchronises the main stream; the draws keep running on theirs)
+		if (rc) return rc;
+	}
+	if (h->tab_C != L.C || h->tab_K < h->K)
+		QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: tables are for %u clusters x %u columns, data has %u x %u", h->tab_K, h->tab_C, h->K, L.C);
+	bool retried = false, batched = false;
+walk_again:
+	batched = h->tab_A != 0;
+	if (batched && h->draws_state != 2) {            // the guess said "line-major" but the tables allow the batched walk
+		rc = start_draws(h, well_seed, true);
+		if (rc) return rc;
+	}
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
-	// Fast path: compact the tables to the A x A box of values that can occur and walk column-synchronously
-	// from shared memory (quantize.cu).  A-1 = max(largest symbol in the rows, largest reachable quantized value).
-	bool batched = false;
-	uint32_t A = 0;
-	{
-		const uint32_t KC = t->clusters * t->columns;
-		QVZ_CUDA(h, cudaMemsetAsync(h->flags + 4, 0, sizeof(int), h->stream));
-		rc = qvz_quantize_vmax(h, KC, h->smax);
-		if (rc) return rc;
-		QVZ_CUDA(h, cudaMemcpyAsync(h->h_flags, h->flags, QVZ_NFLAGS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-		QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
-		uint32_t vmax = (uint32_t) h->h_flags[4] > h->smax ? (uint32_t) h->h_flags[4] : h->smax;
-		A = (vmax + 2) & ~1u;                        // even, >= vmax + 1
-		if (A > 72) A = 72;
-		if (!getenv("QVZ_FORCE_LINE_MAJOR") && qvz_quantize_batched_group(t->clusters, A) > 0) {
-			batched = true;
-			const size_t gbytes = (size_t) t->columns * t->clusters * A * A * 8;
-			if (h->G_cap < gbytes) {
-				free_dev(h->G);
-				h->G = nullptr;
-				QVZ_CUDA(h, cudaMalloc(&h->G, gbytes));
-				h->G_cap = gbytes;
-			}
-			rc = qvz_quantize_compact(h, t->clusters, t->columns, A);
-			if (rc) return rc;
-			if (h->draws_state != 2) {               // the lower bound on A said "line-major" but the tables allow the batched walk
-				rc = start_draws(h, well_seed, true);
-				if (rc) return rc;
-			}
-		}
-	}
 	QVZ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_draws, 0));      // run states (+ draws) are ready
 	qvz_well_debug(h, "after run_states");
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_F], h->stream));
-	if (batched) rc = qvz_quantize_launch_batched(h, t->clusters, A, qv_out != nullptr, toeplitz);
-	else rc = qvz_quantize_launch(h, qv_out != nullptr, 1, toeplitz);
+	if (batched) rc = qvz_quantize_launch_batched(h, h->tab_rows, h->tab_A, qv_out != nullptr, h->tab_dmode);
+	else rc = qvz_quantize_launch(h, qv_out != nullptr, 1, h->tab_dmode);
 	if (rc) return rc;
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));
 	QVZ_CUDA(h, cudaEventRecord(h->ev_walk_done, h->stream));
@@ -710,19 +897,27 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	}
 	qvz_well_debug(h, "end of quantize");
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_D], h->stream));
-	int missing = 0, malformed = 0;
-	rc = take_flag(h, 2, &missing);
+	int missing = 0;
+	rc = take_flag(h, 2, &missing);              // the one host synchronisation of the stage
 	if (rc) return rc;
-	rc = take_flag(h, 3, &malformed);
-	if (rc) return rc;
-	if (malformed) QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: malformed flat tables (context index or quantized value out of range)");
-	// setup = everything on the main stream before the walk (table upload/composition, waiting for the draws);
-	// draws = draw generator kernel on the aux stream (overlapped with the setup); quantize = draws + walk kernel durations
+	if (missing && batched && h->tab_support_used && !retried) {
+		// The images were built for the values the counting stage saw under the cluster ids of THAT time; if the ids have
+		// changed since, a line may need a row that was left out (it then ends in the poison row: never a wrong symbol).
+		// Rebuild the images without that assumption and walk again.
+		rc = build_images(h, false);
+		if (rc) return rc;
+		rc = start_draws(h, well_seed, h->tab_A != 0);
+		if (rc) return rc;
+		retried = true;
+		goto walk_again;
+	}
+	// setup = everything on the main stream before the walk (table upload/composition when tables came with the call, waiting
+	// for the draws); draws = draw generator kernel on the aux stream; quantize = draws + walk kernel durations
 	float draws_ms = 0.f;
 	cudaEventElapsedTime(&draws_ms, h->ev_jump_done, h->ev_draws);      // the draw generator kernel alone (jump-ahead is setup)
 	h->tm.quantize_setup_ms = ev_ms(h, EV_A, EV_F);
-	h->tm.quantize_draws_ms = draws_ms;
-	h->tm.quantize_ms = draws_ms + ev_ms(h, EV_F, EV_C);
+	h->tm.quantize_draws_ms = batched ? draws_ms : 0.f;
+	h->tm.quantize_ms = h->tm.quantize_draws_ms + ev_ms(h, EV_F, EV_C);
 	h->tm.quantize_d2h_ms = ev_ms(h, EV_C, EV_D);
 	if (missing) QVZ_FAIL(h, QVZ_ERR_CONTEXT, "quantize: reached a context without a quantizer (the reference asserts, src/codebook.c:164)");
 	return QVZ_OK;

@@ -235,15 +235,92 @@ qvz_cond_counts_planes_kernel(qvz_layout L, const uint8_t *__restrict__ Xb, uint
 	}
 }
 
-// largest alphabet box whose 32 lane-private copies fit shared memory (42: Phred+33 with Q <= 41)
-static bool planes_possible(const qvz_gpu *h, uint32_t A) {
-	return h->K == 1 && h->Xb && (size_t) A * A * 128 <= 226 * 1024 && !getenv("QVZ_COUNTS_WORDS");
+// Which data values occur per (cluster, column): bit x of support[(k*C + col)*3 + (x >> 5)].  Read off the count table
+// (column marginals over the previous value); the quantize stage uses it to stage only the table rows that the
+// resident rows can reach (quantize.cu).  grid (C, K), 96 threads: thread x, 72 coalesced row reads.
+__global__ void __launch_bounds__(96)
+qvz_cond_counts_support_kernel(uint32_t C, const uint32_t *__restrict__ counts, uint32_t *__restrict__ support)
+{
+	const uint32_t col = blockIdx.x, k = blockIdx.y, x = threadIdx.x;
+	const uint64_t per_cluster = (uint64_t) (1 + 72 * (C - 1)) * 72;
+	const uint32_t *base = counts + k * per_cluster;
+	uint32_t any = 0;
+	if (x < 72) {
+		if (col == 0) any = base[x];
+		else
+			for (uint32_t prev = 0; prev < 72; ++prev) any |= base[(uint64_t) (1 + (col - 1) * 72 + prev) * 72 + x];
+	}
+	const uint32_t m = __ballot_sync(0xFFFFFFFFu, any != 0u);
+	if ((x & 31) == 0) support[((uint64_t) k * C + col) * 3 + (x >> 5)] = m;
+}
+
+int qvz_cond_counts_support(qvz_gpu *h, const uint32_t *counts_dev) {
+	const uint32_t K = h->K, C = h->L.C;
+	const size_t bytes = (size_t) K * C * 3 * sizeof(uint32_t);
+	if (h->support_cap < bytes) {
+		if (h->support) cudaFree(h->support);
+		h->support = nullptr;
+		h->support_cap = 0;
+		QVZ_CUDA(h, cudaMalloc(&h->support, bytes));
+		h->support_cap = bytes;
+	}
+	qvz_cond_counts_support_kernel<<<dim3(C, K), 96, 0, h->stream>>>(C, counts_dev, h->support);
+	QVZ_LAUNCHED(h);
+	QVZ_CUDA(h, cudaGetLastError());
+	h->support_valid = 1;
+	h->support_K = K;
+	return QVZ_OK;
+}
+
+// Xw[c4][p] -> Xb[c][p]: a thread turns the words of 4 consecutive slots into one word per byte plane (4 x 4 byte
+// transpose with byte permutes), so both sides are coalesced.
+__global__ void __launch_bounds__(256)
+qvz_planes_build_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t *__restrict__ Xb)
+{
+	const uint64_t quads = L.P / 4;                      // P % 4096 == 0
+	const uint32_t c4 = blockIdx.y;
+	for (uint64_t q = (uint64_t) blockIdx.x * 256 + threadIdx.x; q < quads; q += (uint64_t) gridDim.x * 256) {
+		const uint4 w = cc_ldg128(Xw + (uint64_t) c4 * L.P + 4 * q);
+		const uint32_t t0 = __byte_perm(w.x, w.y, 0x5140), t1 = __byte_perm(w.z, w.w, 0x5140);
+		const uint32_t t2 = __byte_perm(w.x, w.y, 0x7362), t3 = __byte_perm(w.z, w.w, 0x7362);
+		const uint32_t o[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632), __byte_perm(t2, t3, 0x5410), __byte_perm(t2, t3, 0x7632)};
+#pragma unroll
+		for (uint32_t j = 0; j < 4; ++j)
+			if (4 * c4 + j < L.C) *(uint32_t *) (Xb + (uint64_t) (4 * c4 + j) * L.P + 4 * q) = o[j];
+	}
+}
+
+// The lane-private kernel wants the rows as byte planes: a second copy of the rows, made here the first time a
+// one-cluster count of the resident rows is asked for (and dropped again if the memory is needed: abi.cu).
+// 42 = largest alphabet box whose 32 lane-private copies fit shared memory (Phred+33 with Q <= 41).
+static bool planes_ready(qvz_gpu *h, uint32_t A) {
+	if (h->K != 1 || (size_t) A * A * 128 > 226 * 1024 || getenv("QVZ_COUNTS_WORDS") || getenv("QVZ_NO_PLANES")) return false;
+	const size_t bytes = (size_t) h->L.C * h->L.P;
+	if (!h->Xb || h->Xb_cap < bytes) {
+		if (h->Xb) cudaFree(h->Xb);
+		h->Xb = nullptr;
+		h->Xb_cap = 0;
+		h->Xb_valid = 0;
+		if (cudaMalloc(&h->Xb, bytes) != cudaSuccess) {
+			cudaGetLastError();                          // no room for a second copy: the word-column kernel counts
+			h->Xb = nullptr;
+			return false;
+		}
+		h->Xb_cap = bytes;
+	}
+	if (!h->Xb_valid) {
+		qvz_planes_build_kernel<<<dim3(h->sm_count * 2, h->L.C4), 256, 0, h->stream>>>(h->L, h->Xw, h->Xb);
+		QVZ_LAUNCHED(h);
+		if (cudaGetLastError() != cudaSuccess) return false;
+		h->Xb_valid = 1;
+	}
+	return true;
 }
 
 int qvz_cond_counts_launch(qvz_gpu *h, uint32_t *counts_dev) {
 	const uint32_t K = h->K;
 	const uint32_t A = h->smax + 1 > 72 ? 72 : h->smax + 1;
-	if (planes_possible(h, A)) {
+	if (planes_ready(h, A)) {
 		const size_t smem = (size_t) A * A * 128;
 		QVZ_CUDA(h, cudaMemsetAsync(counts_dev, 0, qvz_gpu_cond_counts_len(1, h->L.C) * sizeof(uint32_t), h->stream));
 		QVZ_CUDA(h, cudaFuncSetAttribute(qvz_cond_counts_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));

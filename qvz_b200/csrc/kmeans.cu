@@ -41,8 +41,9 @@ template <int KT, bool INCR>
 __global__ void __launch_bounds__(QVZ_THREADS)
 qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t *__restrict__ cl,
                          const uint32_t *__restrict__ means_w, const uint32_t *__restrict__ means_sq,
-                         uint32_t Krt, unsigned long long *__restrict__ sums)
+                         uint32_t Krt, unsigned long long *__restrict__ sums, const uint32_t *__restrict__ ctl)
 {
+	if (ctl[QVZ_CTL_DONE]) return;                       // the run has converged: this launch was enqueued speculatively (abi.cu)
 	constexpr int KMAX = KT > 0 ? KT : QVZ_MAX_K;
 	constexpr uint32_t KP = (KMAX + 3) & ~3;             // clusters padded to whole uint4s
 	const uint32_t K = KT > 0 ? (uint32_t) KT : Krt;
@@ -291,15 +292,21 @@ __global__ void __launch_bounds__(QVZ_THREADS)
 qvz_kmeans_update_kernel(uint32_t K, uint32_t C, uint32_t C4, const unsigned long long *__restrict__ sums,
                          uint8_t *__restrict__ means_b, uint32_t *__restrict__ means_w,
                          uint32_t *__restrict__ means_sq, double *__restrict__ moved,
-                         int *__restrict__ flags, int first)
+                         int *__restrict__ flags, int first, uint32_t *__restrict__ ctl, double threshold,
+                         uint32_t max_iter, double *__restrict__ moved_log, unsigned long long *__restrict__ last_counts)
 {
 	__shared__ unsigned long long red_moved[QVZ_THREADS / 32];
 	__shared__ unsigned long long red_sq[QVZ_THREADS / 32];
+	if (!first && ctl[QVZ_CTL_DONE]) return;             // speculative launch after convergence
+	const uint32_t iter = first ? 0u : ctl[QVZ_CTL_ITER];
+	double move_max = 0.0;                               // thread 0 only
+	bool empty = false;
 	for (uint32_t k = 0; k < K; ++k) {
 		unsigned long long count = first ? 1ull : sums[(uint64_t) K * C + k];
 		if (count == 0) {
 			if (threadIdx.x == 0) atomicOr(&flags[1], 1);
 			count = 1;
+			empty = true;
 		}
 		unsigned long long mv = 0, sq = 0;
 		for (uint32_t c = threadIdx.x; c < C; c += QVZ_THREADS) {
@@ -328,7 +335,12 @@ qvz_kmeans_update_kernel(uint32_t K, uint32_t C, uint32_t C4, const unsigned lon
 				a += red_moved[w];
 				b += red_sq[w];
 			}
-			if (!first) moved[k] = (double) a;       // exact: an integer < 2^53, like the reference's double sum
+			if (!first) {
+				moved[k] = (double) a;               // exact: an integer < 2^53, like the reference's double sum
+				if (iter < QVZ_MAX_KMEANS_ITER) moved_log[(size_t) iter * K + k] = (double) a;
+				last_counts[k] = sums[(uint64_t) K * C + k];
+				if ((double) a > move_max) move_max = (double) a;
+			}
 			means_sq[k] = (uint32_t) b;
 		}
 		__syncthreads();
@@ -339,6 +351,12 @@ qvz_kmeans_update_kernel(uint32_t K, uint32_t C, uint32_t C4, const unsigned lon
 			means_w[k * C4 + c4] = w;
 		}
 		__syncthreads();
+	}
+	// do_kmeans_clustering's loop condition, evaluated here so that the host never waits for it:
+	//     loop = moved > cluster_threshold;  while (iter_count < MAX && loop)        (src/cluster.c:221-234)
+	if (!first && threadIdx.x == 0) {
+		ctl[QVZ_CTL_ITER] = iter + 1;
+		if (!(move_max > threshold) || iter + 1 >= max_iter || empty) ctl[QVZ_CTL_DONE] = 1;
 	}
 }
 
@@ -354,11 +372,11 @@ static void launch_assign(qvz_gpu *h, int64_t *sums_dev, unsigned grid, unsigned
 	if (incr) {
 		auto kern = qvz_kmeans_assign_kernel<KT, true>;
 		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		kern<<<grid, R, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K, (unsigned long long *) sums_dev);
+		kern<<<grid, R, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K, (unsigned long long *) sums_dev, h->km_ctl);
 	} else {
 		auto kern = qvz_kmeans_assign_kernel<KT, false>;
 		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		kern<<<grid, R, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K, (unsigned long long *) sums_dev);
+		kern<<<grid, R, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K, (unsigned long long *) sums_dev, h->km_ctl);
 	}
 }
 
@@ -419,10 +437,11 @@ int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev) {
 	return QVZ_OK;
 }
 
-int qvz_kmeans_launch_update(qvz_gpu *h, const int64_t *sums_dev) {
+int qvz_kmeans_launch_update(qvz_gpu *h, const int64_t *sums_dev, double threshold, uint32_t max_iter) {
 	qvz_kmeans_update_kernel<<<1, QVZ_THREADS, 0, h->stream>>>(
 	    h->km_K, h->L.C, h->L.C4, (const unsigned long long *) sums_dev, h->means_b, h->means_w,
-	    h->means_sq, h->moved, h->flags, sums_dev == nullptr);
+	    h->means_sq, h->moved, h->flags, sums_dev == nullptr, h->km_ctl, threshold, max_iter, h->moved_log,
+	    (unsigned long long *) h->last_counts);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;

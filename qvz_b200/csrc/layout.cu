@@ -72,11 +72,20 @@ qvz_ids_to_lines_kernel(qvz_layout L, run_range R, const uint8_t *__restrict__ c
 }
 
 __global__ void __launch_bounds__(QVZ_THREADS)
-qvz_ids_from_lines_kernel(qvz_layout L, run_range R, const uint8_t *__restrict__ stage, uint8_t *__restrict__ cl)
+qvz_ids_from_lines_kernel(qvz_layout L, run_range R, const uint8_t *__restrict__ stage, uint8_t *__restrict__ cl,
+                          uint32_t K, int *__restrict__ flags)
 {
 	uint64_t p, line;
 	if (!range_slot(L, R, (uint64_t) blockIdx.x * QVZ_THREADS + threadIdx.x, p, line)) return;
-	cl[p] = line < L.n_lines ? stage[line - R.line0] : QVZ_NO_LINE;
+	uint32_t id = QVZ_NO_LINE;
+	if (line < L.n_lines) {
+		id = stage[line - R.line0];
+		if (id >= K) {                               // the kernels index their tables with the id: refuse it here
+			atomicOr(&flags[6], 1);
+			id = 0;
+		}
+	}
+	cl[p] = (uint8_t) id;
 }
 
 // Packed words [C4][P] -> line-major bytes (symbol stream, or the `-u` image with '\n' per line).
@@ -134,8 +143,8 @@ int qvz_layout_ids_to_lines(qvz_gpu *h, uint32_t r0, uint32_t nr, uint8_t *stage
 	return QVZ_OK;
 }
 
-int qvz_layout_ids_from_lines(qvz_gpu *h, uint32_t r0, uint32_t nr, const uint8_t *stage_dev) {
-	qvz_ids_from_lines_kernel<<<range_blocks(h, nr), QVZ_THREADS, 0, h->stream>>>(h->L, make_range(h, r0, nr), stage_dev, h->cl);
+int qvz_layout_ids_from_lines(qvz_gpu *h, uint32_t r0, uint32_t nr, const uint8_t *stage_dev, uint32_t K) {
+	qvz_ids_from_lines_kernel<<<range_blocks(h, nr), QVZ_THREADS, 0, h->stream>>>(h->L, make_range(h, r0, nr), stage_dev, h->cl, K, h->flags);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;

@@ -289,27 +289,36 @@ int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int dmode) {
 //                         7-bit draw in the reference's bit server order (4 draws per word, low bits first,
 //                         src/well.c:33-46) and stored in SEQUENCE order, Dw[w*T + run] (coalesced: adjacent
 //                         threads are adjacent runs).  Line i of a run starts at draw i*C: the walk realigns.
-//   qvz_quantize_batched  one CTA walks QB_LINES slots column-synchronously.  The (cluster, column) tables
-//                         are COMPACTED to the A x A box of values that can occur (A-1 = largest symbol /
-//                         quantized value present) and staged per column group in shared memory by TMA bulk
-//                         copies (double buffered, mbarrier completion), so every lookup is one LDS.64;
-//                         each thread carries QB_LPT independent lines (ILP across the dependent
-//                         prev -> lookup -> prev chains).
+//   qvz_quantize_batched  one CTA walks QB_LINES slots column-synchronously.  The tables of a column are ONE
+//                         image of `rows` x A entries per plane, staged in shared memory by TMA bulk copies
+//                         (double buffered, mbarrier completion); each thread carries QB_LPT independent lines
+//                         (ILP across the dependent prev -> lookup -> prev chains).
 //
-// Compact table image, one per column (G[col] = two planes of K*A*A words: lo quantizers, then hi quantizers):
-//   plane[hi][k][prev][data] = variant of that quantizer (the lo/hi choice is known BEFORE the lookup, so only
-//   the chosen 4-byte variant is loaded: one shared-memory wavefront when the lanes' words fall in distinct banks),   variant =
-//       byte 0  qv       the quantized value = the next column's context value (q->q[data])
-//       byte 1  |data-qv| index of the distortion table (72 = poison: NaN / 2^31, see below)
+// Table image of a column (G[col] = two planes, lo quantizers then hi quantizers, of rows x A words):
+//   a ROW is one (cluster, context) pair that some line of the resident rows can reach in this column (row 0 is
+//   the poison row); rows are numbered per column by qvz_quantize_rows_kernel from a forward reachability pass
+//   over the tables, seeded with the data values that occur per (cluster, column) when the counting stage has
+//   seen them (cond_counts.cu: support masks) -- a column's image holds what the walk can touch, not 72 x 72 x K.
+//   plane[hi][row][data] = variant of that quantizer for that input (the lo/hi choice is known BEFORE the
+//   lookup, so only the chosen 4-byte variant is loaded),   variant =
+//       byte 0  qv       the quantized value (q->q[data])
+//       byte 1  row of the NEXT column's image for (this cluster, context qv); 0 = no such context
 //       byte 2  state | hi<<7      the output symbol (q->output_alphabet->indexes[qv], quantizer choice)
-//       byte 3  qratio of the NEXT column's context qv: the draw comparison of the next symbol is
-//               (draw<<24 | 0xFFFFFF) >= variant, with no field extraction at all.
-//   A context the reference would assert on (src/codebook.c:164) has poisoned entries: the line's error sum
-//   becomes NaN (double modes) or >= 2^31 (integer mode) and is reported once per line instead of being
-//   checked per symbol.
+//       byte 3  qratio - 1 of the NEXT column's context qv: the draw comparison of the next symbol is a signed
+//               compare of (draw << 24) with the whole variant, no field extraction at all.
+//   Address of the next lookup = base + 4*raw data byte + 4A*row + H*hi, H = offset of the hi plane = 255*c:
+//       d = previous variant - (draw << 24)      sign bit = hi (draw >= qratio), low 24 bits = the variant's
+//       r = PRMT(row word, d)                     bytes (data, row, hi ? 0xFF : 0, 0)      [sign-replicating selector]
+//       address = dp4a(r, (4, 4A, c, 0), base)
+//   i.e. four integer instructions and the load per symbol.
+//   A context the reference would assert on (src/codebook.c:164) leads to row 0, whose entries lead to row 0 of
+//   the next column: a line that ever got there ends there, and is reported once, after its last column.
+//   The four output bytes / quantized values of a word are gathered with 2 + 2 byte permutes per word; the
+//   distortion of -d M / -d A is VABSDIFF4 + IDP.4A per WORD (exact integers), other matrices add their terms
+//   per symbol in column order (the reference's sequence of double additions).
 // =====================================================================================================
 #ifndef QB_THREADS
-#define QB_THREADS 1024                 // threads per CTA of the walk (tuning: -DQB_THREADS=512 -DQB_CTAS=2)
+#define QB_THREADS 1024                 // threads per CTA of the walk
 #endif
 #ifndef QB_CTAS
 #define QB_CTAS 1                       // resident walk CTAs per SM
@@ -317,7 +326,9 @@ int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int dmode) {
 #define QB_LPT 4
 #define QB_LINES (QB_THREADS * QB_LPT)
 static_assert(QVZ_RUN_ALIGN % QB_LINES == 0, "a step (T slots) must be a whole number of walk batches");
-#define QB_POISON 72u
+#define QB_POISON_ENTRY 0x007F0000u     // qv 0, next row 0, state byte 0x7F (no quantizer has 127 states), ratio byte 0
+#define QB_MAX_ROWS 255u                // the row index travels in one byte
+#define QB_MAX_A 62u                    // 4*A must fit the dp4a coefficient byte
 
 // ---- draw generator ------------------------------------------------------------------------------------
 // one well_1024a step (src/well.c:8-24) at ring position n = (32 - T) & 31, state in registers
@@ -367,7 +378,7 @@ qvz_draws_kernel(qvz_layout L, const uint32_t *__restrict__ run_states, uint32_t
 	if (words & 31) well_turn_seq<0, true>(s, dp, L.T, words & 31);
 }
 
-// largest quantized value any present context can emit for a data value <= smax  -> flags[4]
+// largest quantized value any present context can emit for a data value <= smax  -> *vmax
 __global__ void __launch_bounds__(256)
 qvz_quantize_vmax_kernel(uint64_t entries, const uint32_t *__restrict__ W, const uint8_t *__restrict__ R,
                          uint32_t smax, int *__restrict__ vmax)
@@ -385,38 +396,131 @@ qvz_quantize_vmax_kernel(uint64_t entries, const uint32_t *__restrict__ W, const
 	if ((threadIdx.x & 31) == 0 && m) atomicMax(vmax, (int) m);
 }
 
-// full 72x72 tables -> one contiguous image per COLUMN: G[col] = entry[K][A][A] (see the format above)
+// ---- rows of the column images -----------------------------------------------------------------------------
+// Forward reachability, one CTA per cluster: reach[col][v] = 1 iff some line of this cluster can arrive at column
+// `col` with previous quantized value v.  Column 0: v = 0 (src/qv_compressor.c:89).  Column col+1: every value either
+// quantizer of a reachable, present context of column col emits for a data value that occurs there -- `support`
+// (bit x of word x>>5 of support[(k*C + col)*3 ..]) when the counting stage recorded it, else every x <= smax.
 __global__ void __launch_bounds__(256)
-qvz_quantize_compact_kernel(uint32_t K, uint32_t C, uint32_t A, const uint32_t *__restrict__ W,
-                            const uint8_t *__restrict__ R, uint32_t *__restrict__ G)
+qvz_quantize_reach_kernel(uint32_t C, uint32_t smax, const uint32_t *__restrict__ W, const uint8_t *__restrict__ R,
+                          const uint32_t *__restrict__ support, uint8_t *__restrict__ reach)
+{
+	__shared__ uint32_t cur[72], nxt[72];
+	const uint32_t k = blockIdx.x, tid = threadIdx.x;
+	if (tid < 72) cur[tid] = tid == 0;
+	__syncthreads();
+	for (uint32_t col = 0; col < C; ++col) {
+		const uint64_t kc = (uint64_t) k * C + col;
+		if (tid < 72) {
+			reach[kc * 72 + tid] = (uint8_t) cur[tid];
+			nxt[tid] = 0;
+		}
+		__syncthreads();
+		if (col + 1 < C) {
+			uint32_t sup[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+			if (support) {
+				sup[0] = support[kc * 3 + 0];
+				sup[1] = support[kc * 3 + 1];
+				sup[2] = support[kc * 3 + 2];
+			}
+			for (uint32_t i = tid; i < 72u * (smax + 1); i += 256) {
+				const uint32_t v = i / (smax + 1), x = i - v * (smax + 1);
+				if (cur[v] && R[kc * 72 + v] != 0xFF && ((sup[x >> 5] >> (x & 31)) & 1u)) {
+					const uint32_t e = W[(kc * 72 + v) * 72 + x];
+					nxt[e & 0x7Fu] = 1;              // benign race: everybody writes 1
+					nxt[(e >> 8) & 0x7Fu] = 1;
+				}
+			}
+		}
+		__syncthreads();
+		if (tid < 72) cur[tid] = nxt[tid];
+		__syncthreads();
+	}
+}
+
+// One CTA per column: number the reachable, present (cluster, context) pairs 1, 2, ... in (cluster, value) order
+// -> rowmap[(k*C + col)*72 + v] (0 = no row); the largest row count of any column -> *rows_max (atomicMax).
+// compact = 0: row = 1 + k*A + v for every present context v < A (no reachability pass).
+__global__ void __launch_bounds__(256)
+qvz_quantize_rows_kernel(uint32_t K, uint32_t C, uint32_t A, int compact, const uint8_t *__restrict__ R,
+                         const uint8_t *__restrict__ reach, uint8_t *__restrict__ rowmap, int *__restrict__ rows_max)
+{
+	__shared__ uint32_t warp_tot[8];
+	__shared__ uint32_t carry;
+	const uint32_t col = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) carry = 0;
+	__syncthreads();
+	const uint32_t total = K * 72;
+	for (uint32_t base = 0; base < total; base += 256) {
+		const uint32_t i = base + tid, k = i / 72, v = i - k * 72;
+		const uint64_t kc = (uint64_t) k * C + col;
+		bool on = false;
+		if (i < total) {
+			on = v < A && R[kc * 72 + v] != 0xFF;
+			if (compact) on = on && reach[kc * 72 + v];
+		}
+		uint32_t row = 0;
+		if (compact) {
+			const uint32_t m = __ballot_sync(0xFFFFFFFFu, on);
+			if (lane == 0) warp_tot[warp] = __popc(m);
+			__syncthreads();
+			uint32_t before = carry;
+			for (uint32_t w = 0; w < warp; ++w) before += warp_tot[w];
+			row = on ? 1 + before + __popc(m & ((1u << lane) - 1)) : 0;
+			__syncthreads();
+			if (tid == 0) {
+				uint32_t t = carry;
+				for (uint32_t w = 0; w < 8; ++w) t += warp_tot[w];
+				carry = t;
+			}
+			__syncthreads();
+		} else {
+			row = on ? 1 + k * A + v : 0;
+		}
+		if (i < total) rowmap[kc * 72 + v] = (uint8_t) (row > QB_MAX_ROWS ? 0 : row);
+		if (!compact && on) atomicMax(rows_max, (int) row);
+	}
+	if (compact && tid == 0) atomicMax(rows_max, (int) carry);
+}
+
+__global__ void __launch_bounds__(256)
+qvz_fill_u32_kernel(uint32_t *__restrict__ p, uint64_t n, uint32_t v)
+{
+	for (uint64_t i = (uint64_t) blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t) gridDim.x * 256) p[i] = v;
+}
+
+// full 72x72 tables -> one image per COLUMN (see the format above); G was filled with poison entries before.
+// start[k] = the variant a line of cluster k "comes from" at column 0: row of (k, context 0), qratio of that context.
+__global__ void __launch_bounds__(256)
+qvz_quantize_compact_kernel(uint32_t K, uint32_t C, uint32_t A, uint32_t col_words, uint32_t hi_words, const uint32_t *__restrict__ W,
+                            const uint8_t *__restrict__ R, const uint8_t *__restrict__ rowmap,
+                            uint32_t *__restrict__ G, uint32_t *__restrict__ start)
 {
 	const uint64_t idx = (uint64_t) blockIdx.x * 256 + threadIdx.x;
+	if (idx < K) {
+		const uint64_t kc = idx * C;
+		const uint32_t r0 = R[kc * 72];
+		start[idx] = r0 == 0xFF ? 0u : ((uint32_t) rowmap[kc * 72] << 8) | (((r0 - 1u) & 0xFFu) << 24);
+	}
 	if (idx >= (uint64_t) K * C * A * A) return;
 	const uint32_t x = idx % A, v = (idx / A) % A;
 	const uint64_t kc = idx / ((uint64_t) A * A);
 	const uint32_t k = kc / C, col = kc - (uint64_t) k * C;
-	uint32_t var[2];
-	if (R[kc * 72 + v] == 0xFF) {                    // no such context: poison
-		var[0] = (QB_POISON << 8) | (0x7Fu << 16);
-		var[1] = (QB_POISON << 8) | (0xFFu << 16);
-	} else {
-		const uint32_t e = W[(kc * 72 + v) * 72 + x];
+	const uint32_t row = rowmap[kc * 72 + v];
+	if (row == 0) return;                            // no such context, or nothing gets there
+	const uint32_t e = W[(kc * 72 + v) * 72 + x];
+	uint32_t *g = G + (size_t) col * col_words + (size_t) row * A + x;
 #pragma unroll
-		for (uint32_t hi = 0; hi < 2; ++hi) {
-			const uint32_t qv = (e >> (8 * hi)) & 0xFFu, st = (e >> (16 + 8 * hi)) & 0xFFu;
-			uint32_t nr = 0;
-			if (col + 1 < C) {
-				nr = R[(kc + 1) * 72 + qv];
-				if (nr == 0xFF) nr = 1;              // the poisoned row of the next column reports it
-			}
-			nr = (nr - 1u) & 0xFFu;
-			const uint32_t d = x > qv ? x - qv : qv - x;
-			var[hi] = qv | (d << 8) | (st << 16) | (nr << 24);
+	for (uint32_t hi = 0; hi < 2; ++hi) {
+		const uint32_t qv = (e >> (8 * hi)) & 0xFFu, st = (e >> (16 + 8 * hi)) & 0xFFu;
+		uint32_t nrow = 1, nr = 0;                   // last column: any non-zero row = "the line got through"
+		if (col + 1 < C) {
+			nrow = qv < 72 ? rowmap[(kc + 1) * 72 + qv] : 0;
+			nr = nrow ? R[(kc + 1) * 72 + qv] : 1;
 		}
+		nr = (nr - 1u) & 0xFFu;
+		g[(size_t) hi * hi_words] = nrow ? (qv | (nrow << 8) | (st << 16) | (nr << 24)) : QB_POISON_ENTRY;
 	}
-	uint32_t *g = (uint32_t *) G + (size_t) col * 2 * K * A * A + ((size_t) k * A + v) * A + x;
-	g[0] = var[0];
-	g[(size_t) K * A * A] = var[1];
 }
 
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a): one elected thread moves a whole column-group image
@@ -438,10 +542,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 	    "DONE_%=:\n"
 	    "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-	             ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
 	double v;
 	asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -453,29 +553,47 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 	return v;
 }
 
-// S = columns staged per barrier (4, 2 or 1: the largest whose double buffer fits shared memory)
-// ONEK = one cluster (the reference's default): no per-line table offset
-template <int DMODE, bool WANT_QV, int S, bool ONEK>
+// Geometry of a column image: lo plane (rows*A words), hi plane at byte offset 255*c (c % 4 == 0, >= the lo plane's size),
+// the whole image padded to a multiple of 16 bytes (TMA bulk copy granularity).
+struct qb_geom {
+	uint32_t c2;            // dp4a coefficient of the hi byte
+	uint32_t hi_off;        // bytes
+	uint32_t col_bytes;
+};
+static __host__ __device__ __forceinline__ qb_geom qb_geometry(uint32_t rows, uint32_t A) {
+	qb_geom g;
+	const uint32_t plane = rows * A * 4;
+	g.c2 = ((plane + 254) / 255 + 3) & ~3u;
+	g.hi_off = 255 * g.c2;
+	g.col_bytes = (g.hi_off + plane + 15) & ~15u;
+	return g;
+}
+
+// DM: 0 arbitrary 72x72 matrix (global loads), 1 doubles indexed by |x-y| (-d L), 2 integers indexed by |x-y|,
+//     3 (x-y)^2 (-d M), 4 |x-y| (-d A).      S = columns staged per barrier (4, 2 or 1).
+template <int DM, bool WANT_QV, int S>
 __global__ void __launch_bounds__(QB_THREADS, QB_CTAS)
 qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint32_t *__restrict__ Dw,
                             const uint8_t *__restrict__ cl, const uint8_t *__restrict__ G,
-                            const uint8_t *__restrict__ R, const double *__restrict__ D, uint32_t K,
+                            const uint32_t *__restrict__ start, const double *__restrict__ D, uint32_t rows,
                             uint32_t A, uint32_t *__restrict__ Yw, uint32_t *__restrict__ Qw,
                             double *__restrict__ Ep, int *__restrict__ flags)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
-	// [dd: 73 doubles (or 73 words)][2 mbarriers][buffer 0][buffer 1]; a buffer = S consecutive column images of G
+	// [dd: 72 doubles (or 72 words)][2 mbarriers][buffer 0][buffer 1]; a buffer = S consecutive column images of G
 	constexpr uint32_t DD_WORDS = 2 * (QVZ_ALPHABET + 2);
 	double *dd = (double *) smem;
 	uint32_t *di = smem;
 	uint64_t *full = (uint64_t *) (smem + DD_WORDS);
-	const uint32_t col_bytes = K * A * A * 8;            // multiple of 32 (A is even)
+	const uint32_t A4 = A * 4;
+	const qb_geom geo = qb_geometry(rows, A);
+	const uint32_t col_bytes = geo.col_bytes;
 	const uint32_t buf_bytes = S * col_bytes;
 	const uint32_t buf0 = smem_u32(smem + DD_WORDS + 4);
 	const uint32_t dd_addr = smem_u32(smem);
 	const uint32_t tid = threadIdx.x;
-	if (DMODE == 1 && tid <= QVZ_ALPHABET) dd[tid] = tid < QVZ_ALPHABET ? D[tid] : __longlong_as_double(0x7FF8000000000000ll);
-	if (DMODE == 2 && tid <= QVZ_ALPHABET) di[tid] = tid < QVZ_ALPHABET ? (uint32_t) D[tid] : 0x80000000u;
+	if (DM == 1 && tid < QVZ_ALPHABET) dd[tid] = D[tid];
+	if (DM == 2 && tid < QVZ_ALPHABET) di[tid] = (uint32_t) D[tid];
 	if (tid == 0) {
 		mbar_init(&full[0], 1);
 		mbar_init(&full[1], 1);
@@ -484,8 +602,7 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 	__syncthreads();
 
 	const uint32_t C = L.C, C4 = L.C4;
-	const uint32_t A4 = A * 4;
-	const uint32_t plane = K * A * A4;                   // bytes from a lo variant to its hi variant
+	const uint32_t coef = 4u | (A4 << 8) | (geo.c2 << 16);   // dp4a: 4 * data byte + 4A * row byte + c * (hi ? 255 : 0)
 	uint32_t gcount = 0;                             // column groups consumed so far (uniform): buffer = gcount & 1
 	auto stage = [&](uint32_t col0, uint32_t g) {    // thread 0: columns col0 .. min(col0+S, C)-1 -> buffer g & 1
 		const uint32_t ncol = (C - col0 < (uint32_t) S) ? C - col0 : (uint32_t) S;
@@ -501,24 +618,24 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 	// at the same draw i*C of their runs, so the position in the draw stream is uniform across the CTA.
 	const uint32_t bps = L.T / QB_LINES;                 // batches per step
 	const uint64_t nbatch = (uint64_t) bps * L.Lr;
+	const uint32_t tailmask = (C & 3) ? (0xFFFFFFFFu >> (8 * (4 - (C & 3)))) : 0xFFFFFFFFu;     // live bytes of the last word
 	for (uint64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
 		const uint32_t step = (uint32_t) (batch / bps), boff = (uint32_t) (batch - (uint64_t) step * bps) * QB_LINES;
 		const uint64_t pbase = (uint64_t) step * L.T + boff + tid;
 		const uint32_t d0 = step * C;                    // first draw of these lines within their runs
 		const uint32_t dsh = 8 * (d0 & 3);               // ... = byte d0 & 3 of word d0 >> 2
-		uint32_t koff[QB_LPT], vprev[QB_LPT], erri[QB_LPT];
+		uint32_t vprev[QB_LPT], erri[QB_LPT];
 		double errd[QB_LPT];
 		bool valid[QB_LPT];
 #pragma unroll
 		for (int j = 0; j < QB_LPT; ++j) {
 			const uint32_t kraw = cl[pbase + j * QB_THREADS];
 			valid[j] = kraw != QVZ_NO_LINE;
-			const uint32_t k = valid[j] ? kraw : 0;      // a slot without a line walks cluster 0's tables on zero data
-			koff[j] = ONEK ? 0u : k * A * A4;
-			// column 0: previous value 0 (src/qv_compressor.c:89), its ratio is the first byte of the cluster's R rows
-			vprev[j] = ((uint32_t) __ldg(R + (size_t) k * C * 72) - 1u) << 24;
+			// column 0: previous value 0 (src/qv_compressor.c:89).  A slot without a line walks cluster 0's tables on
+			// symbol 0; wherever that leads (the poison row included) stays inside the image and is not kept.
+			vprev[j] = __ldg(start + (valid[j] ? kraw : 0u));
 			erri[j] = 0;
-			errd[j] = 0.0;
+			errd[j] = 0.0;                               // 0.0 + d == d exactly: same bits as "error = d" at column 0
 		}
 		if (tid == 0) stage(0, gcount);
 		uint32_t xn[QB_LPT], da[QB_LPT], db[QB_LPT];     // draw words w, w+1 of the current step: da is the lower one in even steps, db in odd steps
@@ -540,15 +657,17 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			constexpr bool ODD = decltype(odd_tag)::value;
 			uint32_t (&dlo)[QB_LPT] = ODD ? db : da;
 			uint32_t (&dhi)[QB_LPT] = ODD ? da : db;
-			uint32_t x[QB_LPT], dr[QB_LPT], outw[QB_LPT], qvw[QB_LPT];
+			uint32_t x[QB_LPT], dr[QB_LPT], t01[QB_LPT], t23[QB_LPT], vhold[QB_LPT];
 #pragma unroll
 			for (int j = 0; j < QB_LPT; ++j) {
 				// raw ASCII bytes index the tables directly: the -33 is folded into the table base below.  A slot without
-				// a line (zero words) walks symbol 0 so that every lookup stays inside the tables; nothing of it is kept.
+				// a line (zero words) walks symbol 0 so that every lookup stays inside the image; nothing of it is kept.
 				x[j] = valid[j] ? xn[j] : 0x21212121u;
+				if (TAIL) x[j] = (x[j] & tailmask) | (0x21212121u & ~tailmask);       // columns past C count as symbol 0 (never walked)
 				dr[j] = __funnelshift_r(dlo[j], dhi[j], dsh);    // draws d0 + 4*c4 .. +3 of the run
-				outw[j] = 0;
-				qvw[j] = 0;
+				t01[j] = 0;
+				t23[j] = 0;
+				vhold[j] = 0;
 			}
 			if (!TAIL) {                                 // next word's rows and draws: in flight during this word
 				xr += L.P;
@@ -575,34 +694,58 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 							const uint32_t tab = tabg + sidx * col_bytes - 33u * 4u;       // indexed by the raw byte ('!' + value)
 #pragma unroll
 							for (int j = 0; j < QB_LPT; ++j) {
-								// draw >= qratio  <=>  (int)(draw << 24) > (int)((qratio-1) << 24 | low bits of the previous variant)
-								const int drawt = (int) __byte_perm(dr[j], 0, 0x0444 + (b << 12));
-								const uint32_t base = (drawt > (int) vprev[j]) ? tab + plane : tab;
-								const uint32_t data = __byte_perm(x[j], 0, 0x4440 + b);
-								const uint32_t row = ONEK ? (vprev[j] & 0x7Fu) * A4 : (vprev[j] & 0x7Fu) * A4 + koff[j];
-								const uint32_t v = lds_u32(base + row + data * 4);
-								outw[j] = __byte_perm(outw[j], v, (0x3210 & ~(0xF << (4 * b))) + (6 << (4 * b)));
-								if (WANT_QV) qvw[j] = __byte_perm(qvw[j], v, (0x3210 & ~(0xF << (4 * b))) + (4 << (4 * b)));
-								const uint32_t didx = __byte_perm(v, 0, 0x4441);
-								if (DMODE == 2) erri[j] += lds_u32(dd_addr + didx * 4);
-								else if (DMODE == 1) errd[j] += lds_f64(dd_addr + didx * 8);
-								else if (valid[j]) {
-									if (didx == QB_POISON) missing = true;
-									errd[j] += __ldg(&D[(data - 33u) + 72u * (v & 0x7Fu)]);
-								}
+								// draw >= qratio  <=>  (int)((qratio-1) << 24 | low bits of the previous variant) - (int)(draw << 24) < 0
+								// (exact in 32 bits: the variant is >= -2^24, the draw term <= 127 << 24), and the low 24 bits of the
+								// difference are still the variant's
+								const uint32_t d = vprev[j] - __byte_perm(dr[j], 0, 0x0444 + (b << 12));
+								// byte 0 = raw data byte b of the row word, byte 1 = row byte of the previous variant,
+								// byte 2 = 0xFF if hi (sign of d, replicated), byte 3 = 0 (sign of an ASCII byte)
+								const uint32_t r = __byte_perm(x[j], d, b | (5 << 4) | (0xF << 8) | ((8 | b) << 12));
+								const uint32_t v = lds_u32(__dp4a(r, coef, tab));
+								// gather (qv, state) of the symbol pairs (0,1) and (2,3): bytes [qv_even, qv_odd, st_even, st_odd]
+								if (b == 1) t01[j] = __byte_perm(vhold[j], v, 0x6240);
+								else if (b == 3) t23[j] = __byte_perm(vhold[j], v, 0x6240);
+								else vhold[j] = v;
 								vprev[j] = v;
 							}
 						}
 					}
 				}
 			}
+			uint32_t qvw[QB_LPT];
 #pragma unroll
-			for (int j = 0; j < QB_LPT; ++j) st_stream_u32(yr + j * QB_THREADS, outw[j]);
+			for (int j = 0; j < QB_LPT; ++j) {
+				if (TAIL) {                              // an unpaired last symbol: its partner is "nothing"
+					if ((C & 3) == 1) t01[j] = __byte_perm(vhold[j], 0, 0x6240);
+					if ((C & 3) == 3) t23[j] = __byte_perm(vhold[j], 0, 0x6240);
+				}
+				qvw[j] = __byte_perm(t01[j], t23[j], 0x5410);
+				st_stream_u32(yr + j * QB_THREADS, __byte_perm(t01[j], t23[j], 0x7632));
+			}
 			yr += L.P;
 			if (WANT_QV) {
 #pragma unroll
-				for (int j = 0; j < QB_LPT; ++j) st_stream_u32(qr + j * QB_THREADS, (qvw[j] & 0x7F7F7F7Fu) + 0x21212121u);
+				for (int j = 0; j < QB_LPT; ++j) st_stream_u32(qr + j * QB_THREADS, qvw[j] + 0x21212121u);
 				qr += L.P;
+			}
+			// distortion of this word's symbols (src/qv_compressor.c:97,118): data and quantized values side by side
+#pragma unroll
+			for (int j = 0; j < QB_LPT; ++j) {
+				const uint32_t xq = x[j] - 0x21212121u;      // every byte >= 33: no borrow
+				if (DM == 3 || DM == 4) {
+					const uint32_t d4 = __vabsdiffu4(xq, qvw[j]);
+					erri[j] = __dp4a(d4, DM == 3 ? d4 : 0x01010101u, erri[j]);
+				} else {
+					const uint32_t d4 = DM == 0 ? 0u : __vabsdiffu4(xq, qvw[j]);
+#pragma unroll
+					for (int b = 0; b < 4; ++b) {
+						if (!TAIL || 4 * c4 + b < C) {
+							if (DM == 2) erri[j] += lds_u32(dd_addr + __byte_perm(d4, 0, 0x4440 + b) * 4);
+							else if (DM == 1) errd[j] += lds_f64(dd_addr + __byte_perm(d4, 0, 0x4440 + b) * 8);
+							else if (valid[j]) errd[j] += __ldg(&D[__byte_perm(xq, 0, 0x4440 + b) + 72u * __byte_perm(qvw[j], 0, 0x4440 + b)]);
+						}
+					}
+				}
 			}
 		};
 		uint32_t c4 = 0;
@@ -616,23 +759,26 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 		} else word(c4, std::true_type{}, std::false_type{});
 #pragma unroll
 		for (int j = 0; j < QB_LPT; ++j) {
-			if (DMODE == 2) missing |= valid[j] && erri[j] >= 0x80000000u;
-			if (DMODE == 1) missing |= valid[j] && errd[j] != errd[j];
-			Ep[pbase + j * QB_THREADS] = (DMODE == 2 ? (double) erri[j] : errd[j]) / (double) C;
+			// a line that met a context without a quantizer sits in the poison row (row byte 0) after its last column
+			missing |= valid[j] && (vprev[j] & 0x0000FF00u) == 0u;
+			Ep[pbase + j * QB_THREADS] = ((DM >= 2) ? (double) erri[j] : errd[j]) / (double) C;
 		}
 		__syncthreads();                             // the next batch restages into the other buffer's predecessor
 	}
 	if (missing) atomicOr(&flags[2], 1);
 }
 
-static size_t batched_smem(uint32_t K, uint32_t A, uint32_t S) {
-	return 2 * (QVZ_ALPHABET + 2) * sizeof(uint32_t) + 16 + 2 * (size_t) S * ((size_t) K * A * A * 8);
+static size_t batched_smem(uint32_t rows, uint32_t A, uint32_t S) {
+	return 2 * (QVZ_ALPHABET + 2) * sizeof(uint32_t) + 16 + 2 * (size_t) S * qb_geometry(rows, A).col_bytes;
 }
 
+size_t qvz_quantize_image_bytes(uint32_t C, uint32_t rows, uint32_t A) { return (size_t) C * qb_geometry(rows, A).col_bytes; }
+
 // columns staged per barrier: the largest of 4, 2, 1 whose double buffer fits; 0 = batched path unusable
-uint32_t qvz_quantize_batched_group(uint32_t K, uint32_t A) {
+uint32_t qvz_quantize_batched_group(uint32_t rows, uint32_t A) {
+	if (A > QB_MAX_A || rows > QB_MAX_ROWS + 1) return 0;
 	for (uint32_t S = 4; S >= 1; S >>= 1)
-		if (batched_smem(K, A, S) <= (QB_CTAS == 1 ? 200 : 108) * 1024) return S;
+		if (batched_smem(rows, A, S) <= (QB_CTAS == 1 ? 216 : 108) * 1024) return S;
 	return 0;
 }
 
@@ -651,46 +797,67 @@ int qvz_quantize_vmax(qvz_gpu *h, uint32_t KC, uint32_t smax) {
 	return QVZ_OK;
 }
 
-int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A) {
-	const uint64_t total = (uint64_t) K * C * A * A;
-	qvz_quantize_compact_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, h->stream>>>(K, C, A, h->W, h->R, (uint32_t *) h->G);
+// rowmap (h->rowmap, K*C*72 bytes) and the row count of the fullest column (-> flags[7]); support may be nullptr
+int qvz_quantize_rows(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, int compact, const uint32_t *support) {
+	if (compact) {
+		qvz_quantize_reach_kernel<<<K, 256, 0, h->stream>>>(C, h->smax > 71 ? 71 : h->smax, h->W, h->R, support, h->reach);
+		QVZ_LAUNCHED(h);
+		QVZ_CUDA(h, cudaGetLastError());
+	}
+	qvz_quantize_rows_kernel<<<C, 256, 0, h->stream>>>(K, C, A, compact, h->R, h->reach, h->rowmap, h->flags + 7);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;
 }
 
-template <int DMODE, bool WANT_QV, int S, bool ONEK>
-static void launch_batched(qvz_gpu *h, uint32_t K, uint32_t A) {
-	auto kern = qvz_quantize_batched_kernel<DMODE, WANT_QV, S, ONEK>;
-	const size_t smem = batched_smem(K, A, S);
+// rows = rows per plane of every column image (poison row included)
+int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, uint32_t rows) {
+	const qb_geom geo = qb_geometry(rows, A);
+	const uint64_t words = (uint64_t) C * (geo.col_bytes / 4);
+	qvz_fill_u32_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>((uint32_t *) h->G, words, QB_POISON_ENTRY);
+	QVZ_LAUNCHED(h);
+	const uint64_t total = (uint64_t) K * C * A * A;
+	qvz_quantize_compact_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, h->stream>>>(K, C, A, geo.col_bytes / 4, geo.hi_off / 4, h->W, h->R, h->rowmap, (uint32_t *) h->G, h->start);
+	QVZ_LAUNCHED(h);
+	QVZ_CUDA(h, cudaGetLastError());
+	return QVZ_OK;
+}
+
+template <int DM, bool WANT_QV, int S>
+static void launch_batched(qvz_gpu *h, uint32_t rows, uint32_t A) {
+	auto kern = qvz_quantize_batched_kernel<DM, WANT_QV, S>;
+	const size_t smem = batched_smem(rows, A, S);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	const uint64_t nbatch = (uint64_t) (h->L.T / QB_LINES) * h->L.Lr;     // T % QB_LINES == 0 (QVZ_RUN_ALIGN)
 	const uint64_t resident = (uint64_t) h->sm_count * QB_CTAS;
 	const unsigned grid = (unsigned) (nbatch < resident ? nbatch : resident);
-	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->G, h->R, h->D, K, A, h->Yw,
+	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->G, h->start, h->D, rows, A, h->Yw,
 	                                            WANT_QV ? h->Qw : nullptr, h->Ep, h->flags);
 }
 
-template <int DMODE, bool WANT_QV>
-static void launch_batched_s(qvz_gpu *h, uint32_t K, uint32_t A, uint32_t S) {
-	if (K == 1 && S == 4) launch_batched<DMODE, WANT_QV, 4, true>(h, K, A);
-	else if (K == 1 && S == 2) launch_batched<DMODE, WANT_QV, 2, true>(h, K, A);
-	else if (S == 4) launch_batched<DMODE, WANT_QV, 4, false>(h, K, A);
-	else if (S == 2) launch_batched<DMODE, WANT_QV, 2, false>(h, K, A);
-	else launch_batched<DMODE, WANT_QV, 1, false>(h, K, A);
+template <int DM, bool WANT_QV>
+static void launch_batched_s(qvz_gpu *h, uint32_t rows, uint32_t A, uint32_t S) {
+	if (S == 4) launch_batched<DM, WANT_QV, 4>(h, rows, A);
+	else if (S == 2) launch_batched<DM, WANT_QV, 2>(h, rows, A);
+	else launch_batched<DM, WANT_QV, 1>(h, rows, A);
 }
 
-int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t K, uint32_t A, int want_qv, int dmode) {
-	const uint32_t S = qvz_quantize_batched_group(K, A);
-	if (want_qv) {
-		if (dmode == 2) launch_batched_s<2, true>(h, K, A, S);
-		else if (dmode == 1) launch_batched_s<1, true>(h, K, A, S);
-		else launch_batched_s<0, true>(h, K, A, S);
-	} else {
-		if (dmode == 2) launch_batched_s<2, false>(h, K, A, S);
-		else if (dmode == 1) launch_batched_s<1, false>(h, K, A, S);
-		else launch_batched_s<0, false>(h, K, A, S);
+template <bool WANT_QV>
+static void launch_batched_dm(qvz_gpu *h, uint32_t rows, uint32_t A, uint32_t S, int dm) {
+	switch (dm) {
+	case 4: launch_batched_s<4, WANT_QV>(h, rows, A, S); break;
+	case 3: launch_batched_s<3, WANT_QV>(h, rows, A, S); break;
+	case 2: launch_batched_s<2, WANT_QV>(h, rows, A, S); break;
+	case 1: launch_batched_s<1, WANT_QV>(h, rows, A, S); break;
+	default: launch_batched_s<0, WANT_QV>(h, rows, A, S); break;
 	}
+}
+
+// dm: see the kernel
+int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t rows, uint32_t A, int want_qv, int dm) {
+	const uint32_t S = qvz_quantize_batched_group(rows, A);
+	if (want_qv) launch_batched_dm<true>(h, rows, A, S, dm);
+	else launch_batched_dm<false>(h, rows, A, S, dm);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;

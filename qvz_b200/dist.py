@@ -118,35 +118,36 @@ class ShardedFrontEnd:
         h = self.h
         h.kmeans_begin(init_means)
         if self._sums is None or self._sums.numel() != K * C + K:
-            self._sums = torch.zeros(K * C + K, dtype=torch.int64, device=self.device)
+            # torch.empty, not zeros: the library zeroes / overwrites the buffer itself on ITS stream, and a fill queued
+            # on torch's current stream would not be ordered against that
+            self._sums = torch.empty(K * C + K, dtype=torch.int64, device=self.device)
         sums = self._sums
-        moved_log = []
-        counts = None
-        iters, loop = 0, True
         cuda = self.device.type == "cuda"
-        ev = []
-        if cuda:
-            ext = self._lib_stream()
-        while iters < max_iter and loop:                       # src/cluster.c:221
-            if cuda:
-                ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
-                ev[-1][0].record(ext)
+
+        def enqueue():
             h.kmeans_assign_dev(sums.data_ptr())               # local assignment + local integer sums
-            if cuda:
-                ev[-1][1].record(ext)
-            self._allreduce(sums)                              # global sums (exact)
-            moved, counts = h.kmeans_update_dev(sums.data_ptr())   # recalculate_means on identical data everywhere
-            moved_log.append(moved)
-            loop = float(moved.max()) > threshold              # src/cluster.c:231-233
-            iters += 1
+            self._allreduce(sums)                              # global sums (exact), on the library's stream
+            h.kmeans_update_async(sums.data_ptr(), threshold, max_iter)    # recalculate_means + loop decision, on the device
+
+        # Iteration i+1 is enqueued before anybody looks at the outcome of iteration i.  Every rank sees the same sums,
+        # hence the same decision: all of them enqueue the same collectives in the same order, and launches made after
+        # the run has ended return at once (src/cluster.c:221-234 evaluated in the update kernel).
+        i = 0
+        if max_iter > 0:
+            enqueue()
+            while True:
+                if i + 1 < max_iter:
+                    enqueue()
+                done, _ = h.kmeans_poll(i)
+                if done or i + 1 >= max_iter:
+                    break
+                i += 1
+        iters, moved_log, counts = h.kmeans_result()
         if cuda:
-            end = torch.cuda.Event(enable_timing=True)
-            end.record(ext)
-            end.synchronize()
-            self.kmeans_assign_ms = sum(a.elapsed_time(b) for a, b in ev)
-            self.kmeans_ms = ev[0][0].elapsed_time(end) if ev else 0.0
+            tm = h.timings()
+            self.kmeans_assign_ms, self.kmeans_ms = tm["kmeans_assign_ms"], tm["kmeans_ms"]
         ids, means = h.kmeans_end(want_ids=want_ids)
-        return dict(iters=iters, ids=ids, means=means, counts=counts, moved=np.array(moved_log))
+        return dict(iters=iters, ids=ids, means=means, counts=counts, moved=np.asarray(moved_log))
 
     def cond_counts(self, want_host: bool = True):
         """calculate_statistics' counting loop (reference src/codebook.c:193-205) over all shards;
@@ -154,7 +155,7 @@ class ShardedFrontEnd:
         h = self.h
         n = h.cond_counts_len()
         if self._counts is None or self._counts.numel() != n:
-            self._counts = torch.zeros(n, dtype=torch.int32, device=self.device)
+            self._counts = torch.empty(n, dtype=torch.int32, device=self.device)     # zeroed by the library on its stream
         h.cond_counts_dev(self._counts.data_ptr())
         self._allreduce(self._counts)
         if not want_host:

@@ -334,7 +334,7 @@ int main(int argc, char **argv) {
 		case 'q': extract = 0; i += 1; break;
 		case 'f': need(1); extract = 0; opts.ratio = atof(argv[i + 1]); opts.mode = QVZ_MODE_RATIO; i += 2; break;
 		case 'r': need(1); extract = 0; opts.ratio = atof(argv[i + 1]); opts.mode = QVZ_MODE_FIXED; i += 2; break;
-		case 'c': need(1); opts.clusters = atoi(argv[i + 1]); i += 2; break;
+		case 'c': need(1); opts.clusters = (uint8_t) atoi(argv[i + 1]); i += 2; break;      // qv_options_t.clusters is a uint8_t (include/codebook.h:31)
 		case 'v': opts.verbose = 1; i += 1; break;
 		case 'h': usage(argv[0]); exit(0);
 		case 's': opts.stats = 1; i += 1; break;
@@ -362,8 +362,8 @@ int main(int argc, char **argv) {
 		usage(argv[0]);
 		exit(1);
 	}
-	if (opts.clusters < 1 || opts.clusters > 16) {
-		printf("Between 1 and 16 clusters are supported.\n");
+	if (opts.clusters < 1) {                         // the reference allocates zero clusters and crashes
+		printf("At least one cluster is needed.\n");
 		exit(1);
 	}
 	if (opts.verbose) {

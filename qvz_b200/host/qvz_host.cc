@@ -550,8 +550,9 @@ struct BitWriter {
 	inline void bits(uint32_t v, uint32_t n) {
 		acc = (acc << n) | v;
 		nacc += n;                                   // <= 7 + 32
-		const uint64_t be = __builtin_bswap64(acc << (64 - nacc));      // nacc == 0: shift by 64 would be undefined
-		if (nacc) memcpy(buf.data() + pos, &be, 8);
+		if (nacc == 0) return;                       // nothing pending (n == 0 on a byte boundary): a shift by 64 is undefined
+		const uint64_t be = __builtin_bswap64(acc << (64 - nacc));
+		memcpy(buf.data() + pos, &be, 8);
 		pos += nacc >> 3;
 		nacc &= 7;
 		acc &= (1ull << nacc) - 1;

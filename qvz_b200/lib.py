@@ -25,6 +25,7 @@ EXPORTS = [
     "qvz_gpu_reset_launch_count", "qvz_gpu_load_rows", "qvz_gpu_kmeans", "qvz_gpu_set_clusters",
     "qvz_gpu_kmeans_begin", "qvz_gpu_kmeans_assign_dev", "qvz_gpu_kmeans_update_dev", "qvz_gpu_kmeans_end",
     "qvz_gpu_kmeans_assign_host", "qvz_gpu_kmeans_update_host",
+    "qvz_gpu_kmeans_update_async", "qvz_gpu_kmeans_poll", "qvz_gpu_kmeans_result", "qvz_gpu_upload_tables",
     "qvz_gpu_cond_counts", "qvz_gpu_cond_counts_dev", "qvz_gpu_cond_counts_len", "qvz_gpu_quantize",
     "qvz_gpu_prefetch_draws",
     "qvz_gpu_well_jump",
@@ -109,6 +110,14 @@ def load() -> C.CDLL:
     L.qvz_gpu_kmeans_update_host.argtypes = [vp, i64p, f64p, u32p]
     L.qvz_gpu_kmeans_end.restype = C.c_int
     L.qvz_gpu_kmeans_end.argtypes = [vp, u8p, u8p]
+    L.qvz_gpu_kmeans_update_async.restype = C.c_int
+    L.qvz_gpu_kmeans_update_async.argtypes = [vp, vp, C.c_double, C.c_uint32]
+    L.qvz_gpu_kmeans_poll.restype = C.c_int
+    L.qvz_gpu_kmeans_poll.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int), u32p]
+    L.qvz_gpu_kmeans_result.restype = C.c_int
+    L.qvz_gpu_kmeans_result.argtypes = [vp, u32p, f64p, u32p]
+    L.qvz_gpu_upload_tables.restype = C.c_int
+    L.qvz_gpu_upload_tables.argtypes = [vp, C.POINTER(FlatTablesStruct)]
     L.qvz_gpu_cond_counts.restype = C.c_int
     L.qvz_gpu_cond_counts.argtypes = [vp, u32p]
     L.qvz_gpu_cond_counts_dev.restype = C.c_int
@@ -232,9 +241,18 @@ class Handle:
         sym = symbols_out if symbols_out is not None else (np.empty((n, c), np.uint8) if want_symbols else None)
         qv = qv_out if qv_out is not None else (np.empty((n, c + 1), np.uint8) if want_qv else None)
         err = err_out if err_out is not None else (np.empty(n, np.float64) if want_err else None)
-        st = tables if isinstance(tables, FlatTablesStruct) else tables_struct(tables)
-        self._check(self.L.qvz_gpu_quantize(self.h, C.byref(st), _p(seed, u32p), _addr(sym), _addr(qv), _addr(err)))
+        if tables is None:                     # walk with the tables installed by upload_tables()
+            tp = None
+        else:
+            st = tables if isinstance(tables, FlatTablesStruct) else tables_struct(tables)
+            tp = C.byref(st)
+        self._check(self.L.qvz_gpu_quantize(self.h, tp, _p(seed, u32p), _addr(sym), _addr(qv), _addr(err)))
         return dict(symbols=sym, qv=qv, line_err=err)
+
+    def upload_tables(self, tables):
+        """Install the quantizer tables on the device (stage-3 input); quantize(None, seed) then walks with them."""
+        st = tables if isinstance(tables, FlatTablesStruct) else tables_struct(tables)
+        self._check(self.L.qvz_gpu_upload_tables(self.h, C.byref(st)))
 
     def prefetch_draws(self, seed):
         seed = np.ascontiguousarray(seed, dtype=np.uint32)
@@ -260,6 +278,24 @@ class Handle:
         counts = np.zeros(self.K, np.uint32)
         self._check(self.L.qvz_gpu_kmeans_update_dev(self.h, C.c_void_p(sums_ptr), _p(moved, f64p), _p(counts, u32p)))
         return moved, counts
+
+    def kmeans_update_async(self, sums_ptr: int, threshold: float, max_iter: int):
+        """Recentre and decide on the device whether the loop goes on; does not wait for the GPU."""
+        self._check(self.L.qvz_gpu_kmeans_update_async(self.h, C.c_void_p(sums_ptr), float(threshold), int(max_iter)))
+
+    def kmeans_poll(self, idx: int):
+        """(done, iterations completed) after the idx-th update_async of this run."""
+        done, iters = C.c_int(0), C.c_uint32(0)
+        self._check(self.L.qvz_gpu_kmeans_poll(self.h, idx, C.byref(done), C.byref(iters)))
+        return bool(done.value), int(iters.value)
+
+    def kmeans_result(self, max_rows: int = 1000):
+        """(iterations, moved log [iterations, K], line counts [K]) of the finished run."""
+        iters = C.c_uint32(0)
+        moved = np.zeros((max_rows, self.K), np.float64)
+        counts = np.zeros(self.K, np.uint32)
+        self._check(self.L.qvz_gpu_kmeans_result(self.h, C.byref(iters), _p(moved, f64p), _p(counts, u32p)))
+        return int(iters.value), moved[:min(iters.value, max_rows)], counts
 
     def kmeans_end(self, want_ids=True):
         ids = np.empty(self.n_lines, np.uint8) if want_ids else None
