@@ -130,7 +130,7 @@ static inline run_range make_range(const qvz_gpu *h, uint32_t r0, uint32_t nr) {
 
 int qvz_layout_ingest(qvz_gpu *h, uint32_t r0, uint32_t nr, const uint8_t *stage_dev, uint32_t row_stride) {
 	qvz_ingest_kernel<<<range_blocks(h, nr), QVZ_THREADS, 0, h->stream>>>(h->L, make_range(h, r0, nr), stage_dev, row_stride,
-	                                                                       h->Xw, h->Xb, h->cl, h->flags);
+	                                                                       h->Xw, nullptr /* byte planes are made on first use: cond_counts.cu */, h->cl, h->flags);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;

@@ -542,6 +542,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 	    "DONE_%=:\n"
 	    "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// PTX prmt with the full 4-bit selector nibbles: bit 3 of a nibble replicates the SIGN of the selected byte
+// (__byte_perm keeps only 3 bits per nibble)
+__device__ __forceinline__ uint32_t prmt_full(uint32_t a, uint32_t b, uint32_t sel) {
+	uint32_t d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));      // sel is a constant after unrolling
+	return d;
+}
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
 	double v;
 	asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -700,7 +707,7 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 								const uint32_t d = vprev[j] - __byte_perm(dr[j], 0, 0x0444 + (b << 12));
 								// byte 0 = raw data byte b of the row word, byte 1 = row byte of the previous variant,
 								// byte 2 = 0xFF if hi (sign of d, replicated), byte 3 = 0 (sign of an ASCII byte)
-								const uint32_t r = __byte_perm(x[j], d, b | (5 << 4) | (0xF << 8) | ((8 | b) << 12));
+								const uint32_t r = prmt_full(x[j], d, (uint32_t) (b | (5 << 4) | (0xF << 8) | ((8 | b) << 12)));
 								const uint32_t v = lds_u32(__dp4a(r, coef, tab));
 								// gather (qv, state) of the symbol pairs (0,1) and (2,3): bytes [qv_even, qv_odd, st_even, st_odd]
 								if (b == 1) t01[j] = __byte_perm(vhold[j], v, 0x6240);

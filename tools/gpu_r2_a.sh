@@ -8,7 +8,10 @@ cat /sys/fs/cgroup/memory.max 2>/dev/null
 ulimit -l
 } > gpurun_out/a_env.log 2>&1
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/a_tests.log 2>&1
-echo "tests rc=$?" >> gpurun_out/a_tests.log
+rc=$?
+echo "tests rc=$rc" >> gpurun_out/a_tests.log
+tail -5 gpurun_out/a_tests.log
+if [ $rc -ne 0 ]; then exit 0; fi
 timeout 600 python bench.py --config cfg4 --lines 24000000 --steps 3 --warmup 2 --no-cpu > gpurun_out/a_cfg4_24M.json 2> gpurun_out/a_cfg4_24M.err
 QVZ_NO_SUPPORT=1 timeout 600 python bench.py --config cfg4 --lines 24000000 --steps 3 --warmup 2 --no-cpu --no-parity > gpurun_out/a_cfg4_24M_nosup.json 2> gpurun_out/a_cfg4_24M_nosup.err
 QVZ_NO_REACH=1 timeout 600 python bench.py --config cfg4 --lines 24000000 --steps 3 --warmup 2 --no-cpu --no-parity > gpurun_out/a_cfg4_24M_noreach.json 2> gpurun_out/a_cfg4_24M_noreach.err
