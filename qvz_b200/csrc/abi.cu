@@ -158,6 +158,7 @@ static void release_kmeans(qvz_gpu *h) {
 	free_dev(h->means_b); h->means_b = nullptr;
 	free_dev(h->means_w); h->means_w = nullptr;
 	free_dev(h->means_sq); h->means_sq = nullptr;
+	free_dev(h->means_t); h->means_t = nullptr; h->means_t_cap = 0;
 	free_dev(h->sums); h->sums = nullptr;
 	free_dev(h->moved); h->moved = nullptr;
 	free_dev(h->counts_dev); h->counts_dev = nullptr; h->counts_cached = 0;
@@ -209,6 +210,7 @@ extern "C" int qvz_gpu_open(qvz_gpu **out, int device) {
 	qvz_gpu *h = (qvz_gpu *) calloc(1, sizeof(qvz_gpu));
 	if (!h) return QVZ_ERR_ARG;
 	h->device = device;
+	h->cm_slot = -1;
 	*out = h;       // returned even on failure below so the caller can read last_error, then close
 	QVZ_CUDA(h, cudaSetDevice(device));
 	QVZ_CUDA(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -237,6 +239,7 @@ extern "C" int qvz_gpu_open(qvz_gpu **out, int device) {
 	QVZ_CUDA(h, cudaMemsetAsync(h->flags, 0, QVZ_NFLAGS * sizeof(int), h->stream));
 	QVZ_CUDA(h, cudaMallocHost(&h->h_flags, QVZ_NFLAGS * sizeof(int)));
 	QVZ_CUDA(h, cudaMalloc(&h->D, 72 * 72 * sizeof(double)));
+	h->cm_slot = qvz_kmeans_slot_acquire();
 	return qvz_well_init(h);
 }
 
@@ -259,6 +262,7 @@ extern "C" void qvz_gpu_close(qvz_gpu *h) {
 	}
 	if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
 	release_kmeans(h);
+	qvz_kmeans_slot_release(h->cm_slot);
 	qvz_well_free(h);
 	free_dev(h->W);
 	free_dev(h->flat);
@@ -402,6 +406,11 @@ extern "C" int qvz_gpu_kmeans_begin(qvz_gpu *h, uint32_t K, const uint8_t *init_
 	int rc = ensure_buf(h, &h->means_b, &h->means_b_cap, (size_t) K * C);
 	if (!rc) rc = ensure_buf(h, &h->means_w, &h->means_w_cap, (size_t) K * C4 * sizeof(uint32_t));
 	if (!rc) rc = ensure_buf(h, &h->means_sq, &h->means_sq_cap, K * sizeof(uint32_t));
+	if (!rc && K <= QVZ_MAX_K) {
+		const size_t tb = (size_t) C4 * qvz_kmeans_kp(K) * sizeof(uint32_t);
+		rc = ensure_buf(h, &h->means_t, &h->means_t_cap, tb);
+		if (!rc) QVZ_CUDA(h, cudaMemsetAsync(h->means_t, 0, tb, h->stream));      // the padding centroids are zero words
+	}
 	if (!rc) rc = ensure_buf(h, &h->sums, &h->sums_cap, ((size_t) K * C + K) * sizeof(int64_t));
 	if (!rc) rc = ensure_buf(h, &h->moved, &h->moved_cap, K * sizeof(double));
 	if (!rc) rc = ensure_buf(h, &h->k1_sums, &h->k1_cap, ((size_t) K * C + K) * sizeof(int64_t));   // the run's local running sums
@@ -752,28 +761,32 @@ extern "C" int qvz_gpu_prefetch_draws(qvz_gpu *h, const uint32_t well_seed[32]) 
 // lines can reach.  Synchronises once (the image geometry depends on the tables' content).
 static int build_images(qvz_gpu *h, bool use_support) {
 	const uint32_t K = h->tab_K, C = h->tab_C, A = h->tab_box;
-	uint32_t rows = 0;
+	uint32_t rows = 0, hrows = 0;
+	int compact = 0;
 	h->tab_support_used = 0;
 	if (!getenv("QVZ_FORCE_LINE_MAJOR") && A <= 62) {
-		const int compact = !getenv("QVZ_NO_REACH");
+		compact = !getenv("QVZ_NO_REACH");
 		const uint32_t *support = (use_support && compact && h->support_valid && h->support_K >= K && !getenv("QVZ_NO_SUPPORT")) ? h->support : nullptr;
 		QVZ_CUDA(h, cudaMemsetAsync(h->flags + 7, 0, sizeof(int), h->stream));
+		QVZ_CUDA(h, cudaMemsetAsync(h->flags + 4, 0, sizeof(int), h->stream));
 		int rc = qvz_quantize_rows(h, K, C, A, compact, support);
 		if (rc) return rc;
 		QVZ_CUDA(h, cudaMemcpyAsync(h->h_flags, h->flags, QVZ_NFLAGS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 		QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
 		rows = 1 + (uint32_t) h->h_flags[7];         // + the poison row
-		if (rows > 256 || qvz_quantize_batched_group(rows, A) == 0) rows = 0;
+		hrows = compact ? 1 + (uint32_t) h->h_flags[4] : rows;      // rows of the hi plane: the poison row + the contexts that mix lo and hi
+		if (rows > 256 || qvz_quantize_batched_group(rows, hrows, A) == 0) rows = 0;
 		if (rows && support) h->tab_support_used = 1;
 	}
 	if (rows) {
-		int rc = ensure_buf(h, &h->G, &h->G_cap, qvz_quantize_image_bytes(C, rows, A));
+		int rc = ensure_buf(h, &h->G, &h->G_cap, qvz_quantize_image_bytes(C, rows, hrows, A));
 		if (rc) return rc;
-		rc = qvz_quantize_compact(h, K, C, A, rows);
+		rc = qvz_quantize_compact(h, K, C, A, rows, hrows, compact);
 		if (rc) return rc;
 	}
 	h->tab_A = rows ? A : 0;
 	h->tab_rows = rows;
+	h->tab_hrows = hrows;
 	h->tab_dmode = rows ? h->tab_dm : h->tab_toeplitz;
 	return QVZ_OK;
 }
@@ -868,7 +881,7 @@ walk_again:
 	QVZ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_draws, 0));      // run states (+ draws) are ready
 	qvz_well_debug(h, "after run_states");
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_F], h->stream));
-	if (batched) rc = qvz_quantize_launch_batched(h, h->tab_rows, h->tab_A, qv_out != nullptr, h->tab_dmode);
+	if (batched) rc = qvz_quantize_launch_batched(h, h->tab_rows, h->tab_hrows, h->tab_A, qv_out != nullptr, h->tab_dmode);
 	else rc = qvz_quantize_launch(h, qv_out != nullptr, 1, h->tab_dmode);
 	if (rc) return rc;
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_C], h->stream));

@@ -27,42 +27,76 @@ __device__ __forceinline__ uint4 cc_ldg128(const uint32_t *p) {
 	return v;
 }
 __device__ __forceinline__ void cc_red_shared(uint32_t addr, uint32_t v) {
-	asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+	asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");     // ::cta: no cluster-window address arithmetic
+}
+
+// PTX prmt with the full 4-bit selector nibbles (bit 3 = replicate the sign of the selected byte; __byte_perm keeps 3 bits)
+__device__ __forceinline__ uint32_t cc_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+	uint32_t d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));      // sel is a constant after unrolling
+	return d;
+}
+
+// the 4 slots of one 16-byte load: w4 = this word column, q4 = the previous one, k4 = the 4 cluster ids
+template <bool TAIL>
+__device__ __forceinline__ void cc_count4(const uint4 &w4, const uint4 &q4, uint32_t k4, uint32_t kbase, uint32_t G,
+                                          uint32_t tab_biased, uint32_t live, uint32_t coef, uint32_t slice_bytes, bool single)
+{
+	const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w}, qs[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+	for (int u = 0; u < 4; ++u) {
+		const uint32_t g = ((k4 >> (8 * u)) & 0xFFu) - kbase;          // wraps to a huge value for k < kbase and for 0xFF
+		if (ws[u] != 0u && g < G) {                      // a slot without a line holds zero words (real bytes are >= 33)
+			const uint32_t pv = __funnelshift_r(qs[u], ws[u], 24);         // raw bytes: the previous column's value of bytes 0, 1, 2, 3
+			const uint32_t b0 = single ? tab_biased : tab_biased + g * (4 * slice_bytes);
+#pragma unroll
+			for (uint32_t j = 0; j < 4; ++j) {
+				if (!TAIL || j < live) {
+					// (value, previous, previous, 0) . (4, c1, c2, 0) = 4*value + 4A*previous: the counter's byte offset in its slice
+					// (the '!' offsets of the raw bytes are folded into tab_biased)
+					const uint32_t r = cc_prmt(ws[u], pv, j | ((4 + j) << 4) | ((4 + j) << 8) | ((8 | j) << 12));
+					cc_red_shared(__dp4a(r, coef, b0 + j * slice_bytes), 1u);
+				}
+			}
+		}
+	}
 }
 
 // A thread takes 4 consecutive slots per iteration (16-byte loads of the word column, of the previous word
-// column and one 4-byte load of the cluster ids): 16 symbols per 3 loads.  TAIL = this word column holds
-// the last, partial word of the lines (columns past C must not be counted).
+// column and one 4-byte load of the cluster ids): 16 symbols per 3 loads; the loads of the NEXT iteration are issued
+// before the 16 atomics of the current one.  TAIL = this word column holds the last, partial word of the lines
+// (columns past C must not be counted).
 template <bool TAIL>
 __device__ __forceinline__ void cc_count_chunk(const uint32_t *__restrict__ xc, const uint32_t *__restrict__ xp,
                                                const uint8_t *__restrict__ clp, uint32_t n, bool first, bool single,
                                                uint32_t kbase, uint32_t G, uint32_t tab_addr, uint32_t live,
                                                uint32_t A, uint32_t slice_bytes)
 {
-	const uint32_t row_bytes = A * 4;
-	for (uint32_t i = 4 * threadIdx.x; i < n; i += 4 * CC_THREADS) {
-		const uint4 w4 = cc_ldg128(xc + i);
-		const uint4 q4 = first ? make_uint4(0x21212121u, 0x21212121u, 0x21212121u, 0x21212121u) : cc_ldg128(xp + i);
-		const uint32_t k4 = single ? 0u : __ldg((const uint32_t *) (clp + i));
-		const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w}, qs[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-		for (int u = 0; u < 4; ++u) {
-			const uint32_t g = ((k4 >> (8 * u)) & 0xFFu) - kbase;      // wraps to a huge value for k < kbase and for 0xFF
-			if (ws[u] != 0u && g < G) {                  // a slot without a line holds zero words (real bytes are >= 33)
-				const uint32_t w = ws[u] - 0x21212121u;  // ingest guarantees every real byte >= 33: no borrow
-				const uint32_t pv = __funnelshift_r(qs[u] - 0x21212121u, w, 24);   // bytes: prev of byte 0, 1, 2, 3
-				const uint32_t gb = single ? 0u : g * (4 * slice_bytes);
-				// counter byte offsets of bytes (0, 2) and (1, 3) as 16-bit pairs: (prev*A + cur)*4 <= 71*288 + 284 < 2^16
-				const uint32_t be = (pv & 0x00FF00FFu) * row_bytes + ((w & 0x00FF00FFu) << 2);
-				const uint32_t bo = ((pv >> 8) & 0x00FF00FFu) * row_bytes + (((w >> 8) & 0x00FF00FFu) << 2);
-#pragma unroll
-				for (uint32_t j = 0; j < 4; ++j) {
-					const uint32_t pair = (j & 1) ? bo : be;
-					const uint32_t off = (j & 2) ? pair >> 16 : pair & 0xFFFFu;
-					if (!TAIL || j < live) cc_red_shared(tab_addr + j * slice_bytes + gb + off, 1u);
-				}
-			}
+	const uint32_t A4 = A * 4;                           // <= 288: split over two coefficient bytes
+	const uint32_t c1 = A4 > 252 ? 252 : A4, c2 = A4 - c1;
+	const uint32_t coef = 4u | (c1 << 8) | (c2 << 16);
+	const uint32_t tab_biased = tab_addr - 33u * (4u + A4);
+	const uint4 bang = make_uint4(0x21212121u, 0x21212121u, 0x21212121u, 0x21212121u);
+	uint32_t i = 4 * threadIdx.x;
+	if (i >= n) return;
+	uint4 w4 = cc_ldg128(xc + i), q4 = first ? bang : cc_ldg128(xp + i);
+	uint32_t k4 = single ? 0u : __ldg((const uint32_t *) (clp + i));
+	for (;;) {
+		const uint32_t inext = i + 4 * CC_THREADS;
+		const bool more = inext < n;
+		uint4 w4n = bang, q4n = bang;
+		uint32_t k4n = 0;
+		if (more) {
+			w4n = cc_ldg128(xc + inext);
+			if (!first) q4n = cc_ldg128(xp + inext);
+			if (!single) k4n = __ldg((const uint32_t *) (clp + inext));
 		}
+		cc_count4<TAIL>(w4, q4, k4, kbase, G, tab_biased, live, coef, slice_bytes, single);
+		if (!more) break;
+		w4 = w4n;
+		q4 = q4n;
+		k4 = k4n;
+		i = inext;
 	}
 }
 

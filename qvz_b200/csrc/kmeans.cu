@@ -34,14 +34,22 @@
 //            (A warp-REDUX formulation over sorted rows was measured 2x slower: REDUX.SUM is a slow path.)
 __device__ __forceinline__ uint32_t km_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
+// The packed centroids [C4][KP] in the CONSTANT bank, one slot per handle: every lane of a warp wants the same centroid
+// word at the same time, which the constant cache serves as a uniform operand of the dp4a -- no shared-memory wavefronts
+// (as 16-byte broadcast loads they were two thirds of the kernel's LSU traffic).  The update kernel leaves the packed
+// copy in global memory (means_t); the launch code copies it here device-to-device, in stream order.
+#define KM_CM_SLOTS 8
+#define KM_CM_WORDS 1024
+__constant__ uint32_t c_means[KM_CM_SLOTS * KM_CM_WORDS];
+
 // INCR = a later iteration of a run: sums[] already holds the column sums of the previous assignment, so only the rows
 // whose cluster CHANGED move their bytes (+ new cluster, - old cluster, signed 32-bit partials): no sort, no scatter, no
 // second tile.  Integer sums: the totals are exactly those of a full recount.
-template <int KT, bool INCR>
+template <int KT, bool INCR, bool CM>
 __global__ void __launch_bounds__(QVZ_THREADS)
 qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t *__restrict__ cl,
                          const uint32_t *__restrict__ means_w, const uint32_t *__restrict__ means_sq,
-                         uint32_t Krt, unsigned long long *__restrict__ sums, const uint32_t *__restrict__ ctl)
+                         uint32_t Krt, unsigned long long *__restrict__ sums, const uint32_t *__restrict__ ctl, uint32_t cm_slot)
 {
 	if (ctl[QVZ_CTL_DONE]) return;                       // the run has converged: this launch was enqueued speculatively (abi.cu)
 	constexpr int KMAX = KT > 0 ? KT : QVZ_MAX_K;
@@ -60,10 +68,11 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
 	uint32_t *off = cnt + K;                             // [(NW+1)][K] exclusive offsets, then [K] totals
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	for (uint32_t i = tid; i < C4 * KP; i += R) {
-		const uint32_t c4 = i / KP, k = i - c4 * KP;
-		mean4[i] = k < K ? means_w[k * C4 + c4] : 0u;
-	}
+	if (!CM)
+		for (uint32_t i = tid; i < C4 * KP; i += R) {
+			const uint32_t c4 = i / KP, k = i - c4 * KP;
+			mean4[i] = k < K ? means_w[k * C4 + c4] : 0u;
+		}
 	for (uint32_t i = tid; i < K * C4 * 4; i += R) acc[i] = 0;
 	if (tid < KP) msq[tid] = tid < K ? means_sq[tid] : 0u;
 	if (tid < K) cnt[tid] = 0;
@@ -113,15 +122,22 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
 #pragma unroll 4
 			for (uint32_t c4 = 0; c4 < C4; ++c4) {
 				const uint32_t w = tp[c4 * pitch];
-				const uint4 *m = (const uint4 *) (mean4 + c4 * KP);
+				if (CM) {                                    // centroid words straight from the constant bank (uniform index)
+					const uint32_t *m = c_means + cm_slot * KM_CM_WORDS + c4 * KP;
 #pragma unroll
-				for (uint32_t g = 0; g < KP / 4; ++g) {
-					if (KT > 0 || 4 * g < K) {
-						const uint4 mm = m[g];
-						D[4 * g + 0] = __dp4a(w, mm.x, D[4 * g + 0]);
-						D[4 * g + 1] = __dp4a(w, mm.y, D[4 * g + 1]);
-						D[4 * g + 2] = __dp4a(w, mm.z, D[4 * g + 2]);
-						D[4 * g + 3] = __dp4a(w, mm.w, D[4 * g + 3]);
+					for (uint32_t k = 0; k < (uint32_t) KMAX; ++k)
+						if (KT > 0 || k < K) D[k] = __dp4a(w, m[k], D[k]);
+				} else {
+					const uint4 *m = (const uint4 *) (mean4 + c4 * KP);
+#pragma unroll
+					for (uint32_t g = 0; g < KP / 4; ++g) {
+						if (KT > 0 || 4 * g < K) {
+							const uint4 mm = m[g];
+							D[4 * g + 0] = __dp4a(w, mm.x, D[4 * g + 0]);
+							D[4 * g + 1] = __dp4a(w, mm.y, D[4 * g + 1]);
+							D[4 * g + 2] = __dp4a(w, mm.z, D[4 * g + 2]);
+							D[4 * g + 3] = __dp4a(w, mm.w, D[4 * g + 3]);
+						}
 					}
 				}
 			}
@@ -293,7 +309,8 @@ qvz_kmeans_update_kernel(uint32_t K, uint32_t C, uint32_t C4, const unsigned lon
                          uint8_t *__restrict__ means_b, uint32_t *__restrict__ means_w,
                          uint32_t *__restrict__ means_sq, double *__restrict__ moved,
                          int *__restrict__ flags, int first, uint32_t *__restrict__ ctl, double threshold,
-                         uint32_t max_iter, double *__restrict__ moved_log, unsigned long long *__restrict__ last_counts)
+                         uint32_t max_iter, double *__restrict__ moved_log, unsigned long long *__restrict__ last_counts,
+                         uint32_t *__restrict__ means_t, uint32_t KP)
 {
 	__shared__ unsigned long long red_moved[QVZ_THREADS / 32];
 	__shared__ unsigned long long red_sq[QVZ_THREADS / 32];
@@ -349,6 +366,7 @@ qvz_kmeans_update_kernel(uint32_t K, uint32_t C, uint32_t C4, const unsigned lon
 			for (uint32_t j = 0; j < 4; ++j)
 				if (4 * c4 + j < C) w |= (uint32_t) means_b[k * C + 4 * c4 + j] << (8 * j);
 			means_w[k * C4 + c4] = w;
+			if (means_t) means_t[c4 * KP + k] = w;       // [C4][KP]: the layout the assign kernel reads (constant bank copy)
 		}
 		__syncthreads();
 	}
@@ -367,18 +385,43 @@ static size_t assign_smem(uint32_t K, uint32_t C4, uint32_t R, bool incr = false
 	return words * sizeof(uint32_t);
 }
 
+template <int KT, bool INCR, bool CM>
+static void launch_assign_v(qvz_gpu *h, int64_t *sums_dev, unsigned grid, unsigned R, size_t smem) {
+	auto kern = qvz_kmeans_assign_kernel<KT, INCR, CM>;
+	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	kern<<<grid, R, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K, (unsigned long long *) sums_dev, h->km_ctl,
+	                                   (uint32_t) (h->cm_slot < 0 ? 0 : h->cm_slot));
+}
+
 template <int KT>
-static void launch_assign(qvz_gpu *h, int64_t *sums_dev, unsigned grid, unsigned R, size_t smem, bool incr) {
+static void launch_assign(qvz_gpu *h, int64_t *sums_dev, unsigned grid, unsigned R, size_t smem, bool incr, bool cm) {
 	if (incr) {
-		auto kern = qvz_kmeans_assign_kernel<KT, true>;
-		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		kern<<<grid, R, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K, (unsigned long long *) sums_dev, h->km_ctl);
+		if (cm) launch_assign_v<KT, true, true>(h, sums_dev, grid, R, smem);
+		else launch_assign_v<KT, true, false>(h, sums_dev, grid, R, smem);
 	} else {
-		auto kern = qvz_kmeans_assign_kernel<KT, false>;
-		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		kern<<<grid, R, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_w, h->means_sq, h->km_K, (unsigned long long *) sums_dev, h->km_ctl);
+		if (cm) launch_assign_v<KT, false, true>(h, sums_dev, grid, R, smem);
+		else launch_assign_v<KT, false, false>(h, sums_dev, grid, R, smem);
 	}
 }
+
+// centroid slots of the constant bank: one per live handle of this process (more handles than slots: shared-memory path)
+#include <mutex>
+static std::mutex cm_mutex;
+static bool cm_used[KM_CM_SLOTS];
+int qvz_kmeans_slot_acquire() {
+	std::lock_guard<std::mutex> g(cm_mutex);
+	for (int i = 0; i < KM_CM_SLOTS; ++i)
+		if (!cm_used[i]) {
+			cm_used[i] = true;
+			return i;
+		}
+	return -1;
+}
+void qvz_kmeans_slot_release(int slot) {
+	std::lock_guard<std::mutex> g(cm_mutex);
+	if (slot >= 0 && slot < KM_CM_SLOTS) cm_used[slot] = false;
+}
+uint32_t qvz_kmeans_kp(uint32_t K) { return ((K <= 8 ? K : QVZ_MAX_K) + 3) & ~3u; }      // centroids per column word, padded (kernel: KP)
 
 int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev) {
 	const uint32_t K = h->km_K, C4 = h->L.C4;
@@ -419,15 +462,23 @@ int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev) {
 	const unsigned grid = (unsigned) (blocks < cap ? blocks : cap);
 	int64_t *target = incr ? h->k1_sums : sums_dev;                     // INCR adds signed deltas to the running sums
 	if (!incr) QVZ_CUDA(h, cudaMemsetAsync(sums_dev, 0, sum_bytes, h->stream));
+	// the packed centroids of this iteration -> this handle's slot of the constant bank (device to device, stream ordered)
+	const uint32_t KP = qvz_kmeans_kp(K);
+	// (opt-in: measured SLOWER than the shared-memory broadcast on B200 -- 2.80 vs 2.91 TB/s per iteration on cfg4 --
+	// the LDC operand fetch costs more issue slots than the two LDS.128 it replaces; kept for the record, QVZ_KM_CONST_MEANS=1)
+	const bool cm = getenv("QVZ_KM_CONST_MEANS") && h->cm_slot >= 0 && h->means_t && (size_t) C4 * KP <= KM_CM_WORDS;
+	if (cm)
+		QVZ_CUDA(h, cudaMemcpyToSymbolAsync(c_means, h->means_t, (size_t) C4 * KP * sizeof(uint32_t),
+		                                    (size_t) h->cm_slot * KM_CM_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
 	switch (K) {
-	case 2: launch_assign<2>(h, target, grid, R, smem, incr); break;
-	case 3: launch_assign<3>(h, target, grid, R, smem, incr); break;
-	case 4: launch_assign<4>(h, target, grid, R, smem, incr); break;
-	case 5: launch_assign<5>(h, target, grid, R, smem, incr); break;
-	case 6: launch_assign<6>(h, target, grid, R, smem, incr); break;
-	case 7: launch_assign<7>(h, target, grid, R, smem, incr); break;
-	case 8: launch_assign<8>(h, target, grid, R, smem, incr); break;
-	default: launch_assign<0>(h, target, grid, R, smem, incr); break;
+	case 2: launch_assign<2>(h, target, grid, R, smem, incr, cm); break;
+	case 3: launch_assign<3>(h, target, grid, R, smem, incr, cm); break;
+	case 4: launch_assign<4>(h, target, grid, R, smem, incr, cm); break;
+	case 5: launch_assign<5>(h, target, grid, R, smem, incr, cm); break;
+	case 6: launch_assign<6>(h, target, grid, R, smem, incr, cm); break;
+	case 7: launch_assign<7>(h, target, grid, R, smem, incr, cm); break;
+	case 8: launch_assign<8>(h, target, grid, R, smem, incr, cm); break;
+	default: launch_assign<0>(h, target, grid, R, smem, incr, cm); break;
 	}
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
@@ -441,7 +492,7 @@ int qvz_kmeans_launch_update(qvz_gpu *h, const int64_t *sums_dev, double thresho
 	qvz_kmeans_update_kernel<<<1, QVZ_THREADS, 0, h->stream>>>(
 	    h->km_K, h->L.C, h->L.C4, (const unsigned long long *) sums_dev, h->means_b, h->means_w,
 	    h->means_sq, h->moved, h->flags, sums_dev == nullptr, h->km_ctl, threshold, max_iter, h->moved_log,
-	    (unsigned long long *) h->last_counts);
+	    (unsigned long long *) h->last_counts, h->km_K <= QVZ_MAX_K ? h->means_t : nullptr, qvz_kmeans_kp(h->km_K));
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;

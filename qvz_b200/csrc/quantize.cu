@@ -425,11 +425,12 @@ qvz_quantize_reach_kernel(uint32_t C, uint32_t smax, const uint32_t *__restrict_
 			}
 			for (uint32_t i = tid; i < 72u * (smax + 1); i += 256) {
 				const uint32_t v = i / (smax + 1), x = i - v * (smax + 1);
-				if (cur[v] && R[kc * 72 + v] != 0xFF && ((sup[x >> 5] >> (x & 31)) & 1u)) {
+				const uint32_t ratio = R[kc * 72 + v];
+				if (cur[v] && ratio != 0xFF && ((sup[x >> 5] >> (x & 31)) & 1u)) {
 					const uint32_t e = W[(kc * 72 + v) * 72 + x];
-					nxt[e & 0x7Fu] = 1;              // benign race: everybody writes 1
-					nxt[(e >> 8) & 0x7Fu] = 1;
-				}
+					if (ratio != 0) nxt[e & 0x7Fu] = 1;            // draw >= 0 always: the lo quantizer is never chosen when qratio == 0
+					if (ratio != 128) nxt[(e >> 8) & 0x7Fu] = 1;   // draw <= 127: the hi quantizer is never chosen when qratio == 128
+				}                                                  // (benign race: everybody writes 1)
 			}
 		}
 		__syncthreads();
@@ -438,12 +439,16 @@ qvz_quantize_reach_kernel(uint32_t C, uint32_t smax, const uint32_t *__restrict_
 	}
 }
 
-// One CTA per column: number the reachable, present (cluster, context) pairs 1, 2, ... in (cluster, value) order
-// -> rowmap[(k*C + col)*72 + v] (0 = no row); the largest row count of any column -> *rows_max (atomicMax).
-// compact = 0: row = 1 + k*A + v for every present context v < A (no reachability pass).
+// One CTA per column: number the reachable, present (cluster, context) pairs 1, 2, ... -> rowmap[(k*C + col)*72 + v]
+// (0 = no row).  Contexts that really mix their two quantizers (0 < qratio < 128) come first: only they need an entry in
+// the hi plane -- a context with qratio 128 always takes lo, one with qratio 0 always takes hi (its hi quantizer is stored
+// in the lo plane, see the compact kernel) -- so the hi plane is as long as the mixing rows only.
+// The largest row count of any column -> *rows_max, the largest mixing-row count -> *mixed_max (atomicMax).
+// compact = 0: row = 1 + k*A + v for every present context v < A (no reachability pass, full hi plane).
 __global__ void __launch_bounds__(256)
 qvz_quantize_rows_kernel(uint32_t K, uint32_t C, uint32_t A, int compact, const uint8_t *__restrict__ R,
-                         const uint8_t *__restrict__ reach, uint8_t *__restrict__ rowmap, int *__restrict__ rows_max)
+                         const uint8_t *__restrict__ reach, uint8_t *__restrict__ rowmap, int *__restrict__ rows_max,
+                         int *__restrict__ mixed_max)
 {
 	__shared__ uint32_t warp_tot[8];
 	__shared__ uint32_t carry;
@@ -451,22 +456,34 @@ qvz_quantize_rows_kernel(uint32_t K, uint32_t C, uint32_t A, int compact, const 
 	if (tid == 0) carry = 0;
 	__syncthreads();
 	const uint32_t total = K * 72;
-	for (uint32_t base = 0; base < total; base += 256) {
-		const uint32_t i = base + tid, k = i / 72, v = i - k * 72;
-		const uint64_t kc = (uint64_t) k * C + col;
-		bool on = false;
-		if (i < total) {
-			on = v < A && R[kc * 72 + v] != 0xFF;
-			if (compact) on = on && reach[kc * 72 + v];
+	if (!compact) {
+		for (uint32_t i = tid; i < total; i += 256) {
+			const uint32_t k = i / 72, v = i - k * 72;
+			const uint64_t kc = (uint64_t) k * C + col;
+			const bool on = v < A && R[kc * 72 + v] != 0xFF;
+			const uint32_t row = on ? 1 + k * A + v : 0;
+			rowmap[kc * 72 + v] = (uint8_t) (row > QB_MAX_ROWS ? 0 : row);
+			if (on) atomicMax(rows_max, (int) row);
 		}
-		uint32_t row = 0;
-		if (compact) {
+		return;
+	}
+	for (int pass = 0; pass < 2; ++pass) {               // pass 0: mixing contexts, pass 1: the others
+		for (uint32_t base = 0; base < total; base += 256) {
+			const uint32_t i = base + tid, k = i / 72, v = i - k * 72;
+			const uint64_t kc = (uint64_t) k * C + col;
+			bool on = false;
+			if (i < total) {
+				const uint32_t ratio = R[kc * 72 + v];
+				on = v < A && ratio != 0xFF && reach[kc * 72 + v] && ((ratio != 0 && ratio != 128) == (pass == 0));
+			}
 			const uint32_t m = __ballot_sync(0xFFFFFFFFu, on);
 			if (lane == 0) warp_tot[warp] = __popc(m);
 			__syncthreads();
 			uint32_t before = carry;
 			for (uint32_t w = 0; w < warp; ++w) before += warp_tot[w];
-			row = on ? 1 + before + __popc(m & ((1u << lane) - 1)) : 0;
+			const uint32_t row = 1 + before + __popc(m & ((1u << lane) - 1));
+			if (on) rowmap[kc * 72 + v] = (uint8_t) (row > QB_MAX_ROWS ? 0 : row);
+			else if (i < total && pass == 0) rowmap[kc * 72 + v] = 0;
 			__syncthreads();
 			if (tid == 0) {
 				uint32_t t = carry;
@@ -474,13 +491,10 @@ qvz_quantize_rows_kernel(uint32_t K, uint32_t C, uint32_t A, int compact, const 
 				carry = t;
 			}
 			__syncthreads();
-		} else {
-			row = on ? 1 + k * A + v : 0;
 		}
-		if (i < total) rowmap[kc * 72 + v] = (uint8_t) (row > QB_MAX_ROWS ? 0 : row);
-		if (!compact && on) atomicMax(rows_max, (int) row);
+		if (pass == 0 && tid == 0) atomicMax(mixed_max, (int) carry);
 	}
-	if (compact && tid == 0) atomicMax(rows_max, (int) carry);
+	if (tid == 0) atomicMax(rows_max, (int) carry);
 }
 
 __global__ void __launch_bounds__(256)
@@ -490,16 +504,20 @@ qvz_fill_u32_kernel(uint32_t *__restrict__ p, uint64_t n, uint32_t v)
 }
 
 // full 72x72 tables -> one image per COLUMN (see the format above); G was filled with poison entries before.
+// fold: a context with qratio 128 (always lo) or 0 (always hi) has ONE live quantizer; its variants go to the lo plane
+// (with the hi bit of the output byte saying which quantizer it was) and everybody who leads there carries the ratio
+// byte 127 -- "always lo" -- so the hi plane only holds the rows of contexts that mix (numbered first by the rows kernel).
 // start[k] = the variant a line of cluster k "comes from" at column 0: row of (k, context 0), qratio of that context.
 __global__ void __launch_bounds__(256)
-qvz_quantize_compact_kernel(uint32_t K, uint32_t C, uint32_t A, uint32_t col_words, uint32_t hi_words, const uint32_t *__restrict__ W,
-                            const uint8_t *__restrict__ R, const uint8_t *__restrict__ rowmap,
+qvz_quantize_compact_kernel(uint32_t K, uint32_t C, uint32_t A, uint32_t col_words, uint32_t hi_words, int fold,
+                            const uint32_t *__restrict__ W, const uint8_t *__restrict__ R, const uint8_t *__restrict__ rowmap,
                             uint32_t *__restrict__ G, uint32_t *__restrict__ start)
 {
 	const uint64_t idx = (uint64_t) blockIdx.x * 256 + threadIdx.x;
 	if (idx < K) {
 		const uint64_t kc = idx * C;
-		const uint32_t r0 = R[kc * 72];
+		uint32_t r0 = R[kc * 72];
+		if (fold && (r0 == 0 || r0 == 128)) r0 = 128;
 		start[idx] = r0 == 0xFF ? 0u : ((uint32_t) rowmap[kc * 72] << 8) | (((r0 - 1u) & 0xFFu) << 24);
 	}
 	if (idx >= (uint64_t) K * C * A * A) return;
@@ -508,18 +526,23 @@ qvz_quantize_compact_kernel(uint32_t K, uint32_t C, uint32_t A, uint32_t col_wor
 	const uint32_t k = kc / C, col = kc - (uint64_t) k * C;
 	const uint32_t row = rowmap[kc * 72 + v];
 	if (row == 0) return;                            // no such context, or nothing gets there
+	const uint32_t ratio = R[kc * 72 + v];
 	const uint32_t e = W[(kc * 72 + v) * 72 + x];
 	uint32_t *g = G + (size_t) col * col_words + (size_t) row * A + x;
 #pragma unroll
 	for (uint32_t hi = 0; hi < 2; ++hi) {
+		if (fold && ((ratio == 128 && hi == 1) || (ratio == 0 && hi == 0))) continue;      // never chosen
 		const uint32_t qv = (e >> (8 * hi)) & 0xFFu, st = (e >> (16 + 8 * hi)) & 0xFFu;
-		uint32_t nrow = 1, nr = 0;                   // last column: any non-zero row = "the line got through"
+		uint32_t nrow = 1, nr = 128;                 // last column: any non-zero row = "the line got through"
 		if (col + 1 < C) {
 			nrow = qv < 72 ? rowmap[(kc + 1) * 72 + qv] : 0;
-			nr = nrow ? R[(kc + 1) * 72 + qv] : 1;
+			nr = nrow ? R[(kc + 1) * 72 + qv] : 128;
+			if (fold && nr == 0) nr = 128;           // an always-hi context sits in the lo plane
 		}
 		nr = (nr - 1u) & 0xFFu;
-		g[(size_t) hi * hi_words] = nrow ? (qv | (nrow << 8) | (st << 16) | (nr << 24)) : QB_POISON_ENTRY;
+		const uint32_t var = nrow ? (qv | (nrow << 8) | (st << 16) | (nr << 24)) : QB_POISON_ENTRY;
+		const bool to_lo = hi == 0 || (fold && ratio == 0);
+		g[to_lo ? 0 : hi_words] = var;
 	}
 }
 
@@ -530,6 +553,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 	asm volatile(
@@ -560,19 +586,19 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 	return v;
 }
 
-// Geometry of a column image: lo plane (rows*A words), hi plane at byte offset 255*c (c % 4 == 0, >= the lo plane's size),
+// Geometry of a column image: lo plane (rows*A words), hi plane (hrows*A words) at byte offset 255*c (c % 4 == 0, >= the lo plane's size),
 // the whole image padded to a multiple of 16 bytes (TMA bulk copy granularity).
 struct qb_geom {
 	uint32_t c2;            // dp4a coefficient of the hi byte
 	uint32_t hi_off;        // bytes
 	uint32_t col_bytes;
 };
-static __host__ __device__ __forceinline__ qb_geom qb_geometry(uint32_t rows, uint32_t A) {
+static __host__ __device__ __forceinline__ qb_geom qb_geometry(uint32_t rows, uint32_t hrows, uint32_t A) {
 	qb_geom g;
-	const uint32_t plane = rows * A * 4;
+	const uint32_t plane = rows * A * 4;             // lo plane: every row; hi plane: the first hrows rows (the poison row and the mixing contexts)
 	g.c2 = ((plane + 254) / 255 + 3) & ~3u;
 	g.hi_off = 255 * g.c2;
-	g.col_bytes = (g.hi_off + plane + 15) & ~15u;
+	g.col_bytes = (g.hi_off + hrows * A * 4 + 15) & ~15u;
 	return g;
 }
 
@@ -583,20 +609,24 @@ __global__ void __launch_bounds__(QB_THREADS, QB_CTAS)
 qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint32_t *__restrict__ Dw,
                             const uint8_t *__restrict__ cl, const uint8_t *__restrict__ G,
                             const uint32_t *__restrict__ start, const double *__restrict__ D, uint32_t rows,
-                            uint32_t A, uint32_t *__restrict__ Yw, uint32_t *__restrict__ Qw,
+                            uint32_t hrows, uint32_t A, uint32_t *__restrict__ Yw, uint32_t *__restrict__ Qw,
                             double *__restrict__ Ep, int *__restrict__ flags)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
-	// [dd: 72 doubles (or 72 words)][2 mbarriers][buffer 0][buffer 1]; a buffer = S consecutive column images of G
+	// [dd: 72 doubles (or 72 words)][4 mbarriers][buffer 0][buffer 1]; a buffer = S consecutive column images of G
+	// full[b]: the image has landed (TMA transaction count); empty[b]: every warp is done reading it (one arrival per warp).
+	// There is no CTA-wide barrier in the walk: a warp only waits for the image it needs, and the one thread that issues
+	// the copies waits for the buffer it is about to overwrite.
 	constexpr uint32_t DD_WORDS = 2 * (QVZ_ALPHABET + 2);
 	double *dd = (double *) smem;
 	uint32_t *di = smem;
 	uint64_t *full = (uint64_t *) (smem + DD_WORDS);
+	uint64_t *empty = full + 2;
 	const uint32_t A4 = A * 4;
-	const qb_geom geo = qb_geometry(rows, A);
+	const qb_geom geo = qb_geometry(rows, hrows, A);
 	const uint32_t col_bytes = geo.col_bytes;
 	const uint32_t buf_bytes = S * col_bytes;
-	const uint32_t buf0 = smem_u32(smem + DD_WORDS + 4);
+	const uint32_t buf0 = smem_u32(smem + DD_WORDS + 8);
 	const uint32_t dd_addr = smem_u32(smem);
 	const uint32_t tid = threadIdx.x;
 	if (DM == 1 && tid < QVZ_ALPHABET) dd[tid] = D[tid];
@@ -604,6 +634,8 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 	if (tid == 0) {
 		mbar_init(&full[0], 1);
 		mbar_init(&full[1], 1);
+		mbar_init(&empty[0], QB_THREADS / 32);
+		mbar_init(&empty[1], QB_THREADS / 32);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -611,10 +643,11 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 	const uint32_t C = L.C, C4 = L.C4;
 	const uint32_t coef = 4u | (A4 << 8) | (geo.c2 << 16);   // dp4a: 4 * data byte + 4A * row byte + c * (hi ? 255 : 0)
 	uint32_t gcount = 0;                             // column groups consumed so far (uniform): buffer = gcount & 1
-	auto stage = [&](uint32_t col0, uint32_t g) {    // thread 0: columns col0 .. min(col0+S, C)-1 -> buffer g & 1
+	auto stage = [&](uint32_t col0, uint32_t g) {    // thread 0: columns col0 .. min(col0+S, C)-1 -> buffer g & 1 (its g>>1-th fill)
 		const uint32_t ncol = (C - col0 < (uint32_t) S) ? C - col0 : (uint32_t) S;
 		const uint32_t bytes = ncol * col_bytes;
-		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this buffer are done
+		if (g >= 2) mbar_wait(&empty[g & 1], ((g >> 1) - 1) & 1);      // every warp has finished the buffer's previous image
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... and those generic reads are ordered before the async write
 		mbar_expect_tx(&full[g & 1], bytes);
 		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 		             ::"r"(buf0 + (g & 1) * buf_bytes), "l"(G + (uint64_t) col0 * col_bytes), "r"(bytes), "r"(smem_u32(&full[g & 1])) : "memory");
@@ -664,17 +697,18 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			constexpr bool ODD = decltype(odd_tag)::value;
 			uint32_t (&dlo)[QB_LPT] = ODD ? db : da;
 			uint32_t (&dhi)[QB_LPT] = ODD ? da : db;
-			uint32_t x[QB_LPT], dr[QB_LPT], t01[QB_LPT], t23[QB_LPT], vhold[QB_LPT];
+			uint32_t x[QB_LPT], dr[QB_LPT], t01[QB_LPT], t23[QB_LPT];
 #pragma unroll
 			for (int j = 0; j < QB_LPT; ++j) {
 				// raw ASCII bytes index the tables directly: the -33 is folded into the table base below.  A slot without
 				// a line (zero words) walks symbol 0 so that every lookup stays inside the image; nothing of it is kept.
 				x[j] = valid[j] ? xn[j] : 0x21212121u;
 				if (TAIL) x[j] = (x[j] & tailmask) | (0x21212121u & ~tailmask);       // columns past C count as symbol 0 (never walked)
-				dr[j] = __funnelshift_r(dlo[j], dhi[j], dsh);    // draws d0 + 4*c4 .. +3 of the run
+				// draws d0 + 4*c4 .. +3 of the run.  volatile: stays AHEAD of the loads issued below -- ptxas otherwise hoists those
+				// above it, and the shift then waits on a scoreboard shared with loads that have only just been issued
+				asm volatile("shf.r.wrap.b32 %0, %1, %2, %3;" : "=r"(dr[j]) : "r"(dlo[j]), "r"(dhi[j]), "r"(dsh));
 				t01[j] = 0;
 				t23[j] = 0;
-				vhold[j] = 0;
 			}
 			if (!TAIL) {                                 // next word's rows and draws: in flight during this word
 				xr += L.P;
@@ -689,7 +723,6 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			for (int g = 0; g < 4 / S; ++g) {            // the column groups (= staged images) inside this word
 				const uint32_t col0 = 4 * c4 + g * S;
 				if (!TAIL || col0 < C) {
-					__syncthreads();                     // everyone is done with the previous group: its buffer is free
 					if (tid == 0 && col0 + S < C) stage(col0 + S, gcount + 1);
 					mbar_wait(&full[gcount & 1], (gcount >> 1) & 1);   // this group's image has landed
 					const uint32_t tabg = buf0 + (gcount & 1) * buf_bytes;
@@ -710,21 +743,23 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 								const uint32_t r = prmt_full(x[j], d, (uint32_t) (b | (5 << 4) | (0xF << 8) | ((8 | b) << 12)));
 								const uint32_t v = lds_u32(__dp4a(r, coef, tab));
 								// gather (qv, state) of the symbol pairs (0,1) and (2,3): bytes [qv_even, qv_odd, st_even, st_odd]
-								if (b == 1) t01[j] = __byte_perm(vhold[j], v, 0x6240);
-								else if (b == 3) t23[j] = __byte_perm(vhold[j], v, 0x6240);
-								else vhold[j] = v;
+								// (the even symbol's variant is still in vprev when the odd one arrives)
+								if (b == 1) t01[j] = __byte_perm(vprev[j], v, 0x6240);
+								else if (b == 3) t23[j] = __byte_perm(vprev[j], v, 0x6240);
 								vprev[j] = v;
 							}
 						}
 					}
+					__syncwarp();                        // this warp is done with the group's image
+					if ((tid & 31) == 0) mbar_arrive(&empty[(gcount - 1) & 1]);
 				}
 			}
 			uint32_t qvw[QB_LPT];
 #pragma unroll
 			for (int j = 0; j < QB_LPT; ++j) {
-				if (TAIL) {                              // an unpaired last symbol: its partner is "nothing"
-					if ((C & 3) == 1) t01[j] = __byte_perm(vhold[j], 0, 0x6240);
-					if ((C & 3) == 3) t23[j] = __byte_perm(vhold[j], 0, 0x6240);
+				if (TAIL) {                              // an unpaired last symbol (still in vprev): its partner is "nothing"
+					if ((C & 3) == 1) t01[j] = __byte_perm(vprev[j], 0, 0x6240);
+					if ((C & 3) == 3) t23[j] = __byte_perm(vprev[j], 0, 0x6240);
 				}
 				qvw[j] = __byte_perm(t01[j], t23[j], 0x5410);
 				st_stream_u32(yr + j * QB_THREADS, __byte_perm(t01[j], t23[j], 0x7632));
@@ -770,22 +805,21 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			missing |= valid[j] && (vprev[j] & 0x0000FF00u) == 0u;
 			Ep[pbase + j * QB_THREADS] = ((DM >= 2) ? (double) erri[j] : errd[j]) / (double) C;
 		}
-		__syncthreads();                             // the next batch restages into the other buffer's predecessor
 	}
 	if (missing) atomicOr(&flags[2], 1);
 }
 
-static size_t batched_smem(uint32_t rows, uint32_t A, uint32_t S) {
-	return 2 * (QVZ_ALPHABET + 2) * sizeof(uint32_t) + 16 + 2 * (size_t) S * qb_geometry(rows, A).col_bytes;
+static size_t batched_smem(uint32_t rows, uint32_t hrows, uint32_t A, uint32_t S) {
+	return 2 * (QVZ_ALPHABET + 2) * sizeof(uint32_t) + 32 + 2 * (size_t) S * qb_geometry(rows, hrows, A).col_bytes;
 }
 
-size_t qvz_quantize_image_bytes(uint32_t C, uint32_t rows, uint32_t A) { return (size_t) C * qb_geometry(rows, A).col_bytes; }
+size_t qvz_quantize_image_bytes(uint32_t C, uint32_t rows, uint32_t hrows, uint32_t A) { return (size_t) C * qb_geometry(rows, hrows, A).col_bytes; }
 
 // columns staged per barrier: the largest of 4, 2, 1 whose double buffer fits; 0 = batched path unusable
-uint32_t qvz_quantize_batched_group(uint32_t rows, uint32_t A) {
+uint32_t qvz_quantize_batched_group(uint32_t rows, uint32_t hrows, uint32_t A) {
 	if (A > QB_MAX_A || rows > QB_MAX_ROWS + 1) return 0;
 	for (uint32_t S = 4; S >= 1; S >>= 1)
-		if (batched_smem(rows, A, S) <= (QB_CTAS == 1 ? 216 : 108) * 1024) return S;
+		if (batched_smem(rows, hrows, A, S) <= (QB_CTAS == 1 ? 226 : 112) * 1024) return S;       // 227 KB per CTA on sm_100
 	return 0;
 }
 
@@ -804,67 +838,68 @@ int qvz_quantize_vmax(qvz_gpu *h, uint32_t KC, uint32_t smax) {
 	return QVZ_OK;
 }
 
-// rowmap (h->rowmap, K*C*72 bytes) and the row count of the fullest column (-> flags[7]); support may be nullptr
+// rowmap (h->rowmap, K*C*72 bytes), the row count of the fullest column (-> flags[7]) and its mixing-row count (-> flags[4]); support may be nullptr
 int qvz_quantize_rows(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, int compact, const uint32_t *support) {
 	if (compact) {
 		qvz_quantize_reach_kernel<<<K, 256, 0, h->stream>>>(C, h->smax > 71 ? 71 : h->smax, h->W, h->R, support, h->reach);
 		QVZ_LAUNCHED(h);
 		QVZ_CUDA(h, cudaGetLastError());
 	}
-	qvz_quantize_rows_kernel<<<C, 256, 0, h->stream>>>(K, C, A, compact, h->R, h->reach, h->rowmap, h->flags + 7);
+	qvz_quantize_rows_kernel<<<C, 256, 0, h->stream>>>(K, C, A, compact, h->R, h->reach, h->rowmap, h->flags + 7, h->flags + 4);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;
 }
 
 // rows = rows per plane of every column image (poison row included)
-int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, uint32_t rows) {
-	const qb_geom geo = qb_geometry(rows, A);
+int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, uint32_t rows, uint32_t hrows, int fold) {
+	const qb_geom geo = qb_geometry(rows, hrows, A);
 	const uint64_t words = (uint64_t) C * (geo.col_bytes / 4);
 	qvz_fill_u32_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>((uint32_t *) h->G, words, QB_POISON_ENTRY);
 	QVZ_LAUNCHED(h);
 	const uint64_t total = (uint64_t) K * C * A * A;
-	qvz_quantize_compact_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, h->stream>>>(K, C, A, geo.col_bytes / 4, geo.hi_off / 4, h->W, h->R, h->rowmap, (uint32_t *) h->G, h->start);
+	qvz_quantize_compact_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, h->stream>>>(K, C, A, geo.col_bytes / 4, geo.hi_off / 4, fold, h->W, h->R, h->rowmap, (uint32_t *) h->G, h->start);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;
 }
 
 template <int DM, bool WANT_QV, int S>
-static void launch_batched(qvz_gpu *h, uint32_t rows, uint32_t A) {
+static void launch_batched(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_t A) {
 	auto kern = qvz_quantize_batched_kernel<DM, WANT_QV, S>;
-	const size_t smem = batched_smem(rows, A, S);
+	const size_t smem = batched_smem(rows, hrows, A, S);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	const uint64_t nbatch = (uint64_t) (h->L.T / QB_LINES) * h->L.Lr;     // T % QB_LINES == 0 (QVZ_RUN_ALIGN)
 	const uint64_t resident = (uint64_t) h->sm_count * QB_CTAS;
 	const unsigned grid = (unsigned) (nbatch < resident ? nbatch : resident);
-	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->G, h->start, h->D, rows, A, h->Yw,
+	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->G, h->start, h->D, rows, hrows, A, h->Yw,
 	                                            WANT_QV ? h->Qw : nullptr, h->Ep, h->flags);
 }
 
 template <int DM, bool WANT_QV>
-static void launch_batched_s(qvz_gpu *h, uint32_t rows, uint32_t A, uint32_t S) {
-	if (S == 4) launch_batched<DM, WANT_QV, 4>(h, rows, A);
-	else if (S == 2) launch_batched<DM, WANT_QV, 2>(h, rows, A);
-	else launch_batched<DM, WANT_QV, 1>(h, rows, A);
+static void launch_batched_s(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_t A, uint32_t S) {
+	if (S == 4) launch_batched<DM, WANT_QV, 4>(h, rows, hrows, A);
+	else if (S == 2) launch_batched<DM, WANT_QV, 2>(h, rows, hrows, A);
+	else launch_batched<DM, WANT_QV, 1>(h, rows, hrows, A);
 }
 
 template <bool WANT_QV>
-static void launch_batched_dm(qvz_gpu *h, uint32_t rows, uint32_t A, uint32_t S, int dm) {
+static void launch_batched_dm(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_t A, uint32_t S, int dm) {
 	switch (dm) {
-	case 4: launch_batched_s<4, WANT_QV>(h, rows, A, S); break;
-	case 3: launch_batched_s<3, WANT_QV>(h, rows, A, S); break;
-	case 2: launch_batched_s<2, WANT_QV>(h, rows, A, S); break;
-	case 1: launch_batched_s<1, WANT_QV>(h, rows, A, S); break;
-	default: launch_batched_s<0, WANT_QV>(h, rows, A, S); break;
+	case 4: launch_batched_s<4, WANT_QV>(h, rows, hrows, A, S); break;
+	case 3: launch_batched_s<3, WANT_QV>(h, rows, hrows, A, S); break;
+	case 2: launch_batched_s<2, WANT_QV>(h, rows, hrows, A, S); break;
+	case 1: launch_batched_s<1, WANT_QV>(h, rows, hrows, A, S); break;
+	default: launch_batched_s<0, WANT_QV>(h, rows, hrows, A, S); break;
 	}
 }
 
 // dm: see the kernel
-int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t rows, uint32_t A, int want_qv, int dm) {
-	const uint32_t S = qvz_quantize_batched_group(rows, A);
-	if (want_qv) launch_batched_dm<true>(h, rows, A, S, dm);
-	else launch_batched_dm<false>(h, rows, A, S, dm);
+int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_t A, int want_qv, int dm) {
+	const uint32_t S = qvz_quantize_batched_group(rows, hrows, A);
+	if (getenv("QVZ_DEBUG_WALK")) fprintf(stderr, "[walk] rows %u hi rows %u A %u S %u smem %zu dm %d\n", rows, hrows, A, S, batched_smem(rows, hrows, A, S), dm);
+	if (want_qv) launch_batched_dm<true>(h, rows, hrows, A, S, dm);
+	else launch_batched_dm<false>(h, rows, hrows, A, S, dm);
 	QVZ_LAUNCHED(h);
 	QVZ_CUDA(h, cudaGetLastError());
 	return QVZ_OK;

@@ -69,6 +69,9 @@ struct qvz_gpu {
 	uint8_t *means_b;        // [K][C] current centroids (raw ASCII bytes)
 	uint32_t *means_w;       // [K][C4] same, packed for dp4a (zero padded)
 	uint32_t *means_sq;      // [K] sum of squares of each centroid
+	uint32_t *means_t;       // [C4][KP] the packed centroids transposed and padded: what the assign kernel reads (kmeans.cu: constant bank copy)
+	size_t means_t_cap;
+	int cm_slot;             // this handle's centroid slot of the constant bank, -1 = none
 	int64_t *sums;           // [K*C + K] column sums, then line counts
 	int64_t *k1_sums;        // this shard's running sums of the current k-means run (kmeans.cu): K == 1 reuses them, K >= 2 updates them
 	size_t k1_cap;
@@ -126,7 +129,7 @@ struct qvz_gpu {
 	size_t Xw_cap, cl_cap, Yw_cap, Qw_cap, Dw_cap, Ep_cap, rs_cap;
 
 	// quantizer tables resident on the device (qvz_gpu_upload_tables)
-	uint32_t tab_K, tab_C, tab_A, tab_rows;    // tab_A = 0: the line-major walk (W / R only)
+	uint32_t tab_K, tab_C, tab_A, tab_rows, tab_hrows;    // tab_A = 0: the line-major walk (W / R only)
 	uint32_t tab_box;                // alphabet box of the images: > every symbol of the rows and every value a quantizer can emit for one
 	int tab_dmode, tab_valid, tab_toeplitz, tab_dm, tab_support_used;
 
@@ -165,6 +168,9 @@ int qvz_layout_doubles_to_lines(qvz_gpu *h, uint32_t r0, uint32_t nr, const doub
 
 // kmeans.cu
 int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev);
+int qvz_kmeans_slot_acquire();
+void qvz_kmeans_slot_release(int slot);
+uint32_t qvz_kmeans_kp(uint32_t K);
 int qvz_kmeans_launch_assign_wide(qvz_gpu *h, int64_t *sums_dev);      // kmeans_wide.cu: more than QVZ_MAX_K clusters
 int qvz_kmeans_launch_update(qvz_gpu *h, const int64_t *sums_dev, double threshold, uint32_t max_iter);
 
@@ -184,9 +190,9 @@ int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int toeplitz);
 int qvz_quantize_draws(qvz_gpu *h);
 int qvz_quantize_vmax(qvz_gpu *h, uint32_t KC, uint32_t smax);
 int qvz_quantize_rows(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, int compact, const uint32_t *support);
-int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, uint32_t rows);
-uint32_t qvz_quantize_batched_group(uint32_t rows, uint32_t A);
-size_t qvz_quantize_image_bytes(uint32_t C, uint32_t rows, uint32_t A);
-int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t rows, uint32_t A, int want_qv, int dm);
+int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, uint32_t rows, uint32_t hrows, int fold);
+uint32_t qvz_quantize_batched_group(uint32_t rows, uint32_t hrows, uint32_t A);
+size_t qvz_quantize_image_bytes(uint32_t C, uint32_t rows, uint32_t hrows, uint32_t A);
+int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_t A, int want_qv, int dm);
 int qvz_quantize_compose(qvz_gpu *h, uint32_t KC, const uint32_t *nctx, const uint8_t *ctx_of, const uint64_t *q_off,
                          const uint8_t *qratio, const uint8_t *qmap, const uint8_t *smap);
