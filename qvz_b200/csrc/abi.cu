@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
 #include <vector>
 
 #include "qvz_internal.cuh"
@@ -61,6 +62,7 @@ static int ensure_stage(qvz_gpu *h, size_t min_bytes) {
 	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
 	QVZ_CUDA(h, cudaStreamSynchronize(h->copy_stream));
 	for (int b = 0; b < 2; ++b) {
+		if (h->pin[b]) cudaFreeHost(h->pin[b]);
 		free_dev(h->stage[b]);
 		h->stage[b] = nullptr;
 		QVZ_CUDA(h, cudaMalloc(&h->stage[b], want));
@@ -101,20 +103,70 @@ static piece make_piece(const qvz_gpu *h, uint32_t r0, uint32_t per, int k) {
 	return pc;
 }
 
-// host -> device.  consume(piece, staged bytes) launches the re-layout kernel on h->stream.
+// Host side of a piece.  Pinned (or registered) memory is handed to the copy engine as it is.  Pageable memory -- an
+// mmap'ed file, a malloc'ed output array: what the reference's callers have (src/lines.c:62-79) -- goes through one of two
+// PINNED bounce buffers, filled or drained by a few host threads while the other buffer's DMA is in flight: the driver's
+// own path for pageable memory is a single-threaded staged copy.
+static bool host_is_pinned(const void *p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static void par_memcpy(void *dst, const void *src, size_t n) {
+	unsigned nt = std::thread::hardware_concurrency() / 2;
+	if (const char *e = getenv("QVZ_COPY_THREADS")) nt = (unsigned) atoi(e);
+	if (nt > 8) nt = 8;
+	if (nt < 2 || n < ((size_t) 8 << 20)) {
+		memcpy(dst, src, n);
+		return;
+	}
+	const size_t per = ((n + nt - 1) / nt + 4095) & ~(size_t) 4095;
+	std::vector<std::thread> pool;
+	for (unsigned t = 0; t < nt; ++t) {
+		const size_t lo = (size_t) t * per, hi = lo + per < n ? lo + per : n;
+		if (lo >= hi) break;
+		pool.emplace_back([=]() { memcpy((char *) dst + lo, (const char *) src + lo, hi - lo); });
+	}
+	for (auto &t : pool) t.join();
+}
+
+static int ensure_pin(qvz_gpu *h) {
+	if (h->pin[0] && h->pin_bytes >= h->stage_bytes) return QVZ_OK;
+	for (int b = 0; b < 2; ++b) {
+		if (h->pin[b]) cudaFreeHost(h->pin[b]);
+		h->pin[b] = nullptr;
+		QVZ_CUDA(h, cudaMallocHost(&h->pin[b], h->stage_bytes));
+	}
+	h->pin_bytes = h->stage_bytes;
+	return QVZ_OK;
+}
+
+// host -> device.  consume(piece) launches the re-layout kernel on h->stream.
 template <class F>
 static int pipeline_h2d(qvz_gpu *h, const uint8_t *host, size_t stride, size_t row_bytes, F consume) {
 	uint32_t per = 0;
 	int rc = plan_pieces(h, stride, &per);
 	if (rc) return rc;
+	const bool bounce = !host_is_pinned(host) && !getenv("QVZ_NO_BOUNCE");
+	if (bounce && (rc = ensure_pin(h))) return rc;
 	bool used[2] = {false, false};
 	int k = 0;
 	for (uint32_t r0 = 0; r0 < h->L.T; r0 += per, ++k) {
 		const piece pc = make_piece(h, r0, per, k);
 		if (pc.l1 > pc.l0) {
 			const size_t bytes = (size_t) (pc.l1 - pc.l0 - 1) * stride + row_bytes;
+			const uint8_t *src = host + (size_t) pc.l0 * stride;
+			if (bounce) {
+				if (used[pc.buf]) QVZ_CUDA(h, cudaEventSynchronize(h->ev_copied[pc.buf]));   // the DMA out of this bounce buffer is done
+				par_memcpy(h->pin[pc.buf], src, bytes);
+				src = h->pin[pc.buf];
+			}
 			if (used[pc.buf]) QVZ_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[pc.buf], 0));
-			QVZ_CUDA(h, cudaMemcpyAsync(h->stage[pc.buf], host + (size_t) pc.l0 * stride, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+			QVZ_CUDA(h, cudaMemcpyAsync(h->stage[pc.buf], src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
 			QVZ_CUDA(h, cudaEventRecord(h->ev_copied[pc.buf], h->copy_stream));
 			QVZ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_copied[pc.buf], 0));
 		}
@@ -134,7 +186,19 @@ static int pipeline_d2h(qvz_gpu *h, uint8_t *host, size_t stride, size_t row_byt
 	uint32_t per = 0;
 	int rc = plan_pieces(h, stride, &per);
 	if (rc) return rc;
+	const bool bounce = !host_is_pinned(host) && !getenv("QVZ_NO_BOUNCE");
+	if (bounce && (rc = ensure_pin(h))) return rc;
 	bool used[2] = {false, false};
+	uint8_t *pend_dst = nullptr;                     // bounce: the piece whose DMA has been enqueued but not yet drained to `host`
+	size_t pend_bytes = 0;
+	int pend_buf = 0;
+	auto drain = [&]() -> int {
+		if (!pend_dst) return QVZ_OK;
+		QVZ_CUDA(h, cudaEventSynchronize(h->ev_consumed[pend_buf]));
+		par_memcpy(pend_dst, h->pin[pend_buf], pend_bytes);
+		pend_dst = nullptr;
+		return QVZ_OK;
+	};
 	int k = 0;
 	for (uint32_t r0 = 0; r0 < h->L.T; r0 += per, ++k) {
 		const piece pc = make_piece(h, r0, per, k);
@@ -145,10 +209,21 @@ static int pipeline_d2h(qvz_gpu *h, uint8_t *host, size_t stride, size_t row_byt
 		QVZ_CUDA(h, cudaEventRecord(h->ev_copied[pc.buf], h->stream));
 		QVZ_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copied[pc.buf], 0));
 		const size_t bytes = (size_t) (pc.l1 - pc.l0 - 1) * stride + row_bytes;
-		QVZ_CUDA(h, cudaMemcpyAsync(host + (size_t) pc.l0 * stride, h->stage[pc.buf], bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+		uint8_t *dst = host + (size_t) pc.l0 * stride;
+		// (bounce: pin[pc.buf] was drained before piece k-1 was enqueued, i.e. before this point)
+		QVZ_CUDA(h, cudaMemcpyAsync(bounce ? h->pin[pc.buf] : dst, h->stage[pc.buf], bytes, cudaMemcpyDeviceToHost, h->copy_stream));
 		QVZ_CUDA(h, cudaEventRecord(h->ev_consumed[pc.buf], h->copy_stream));
 		used[pc.buf] = true;
+		if (bounce) {
+			rc = drain();                            // piece k-1 -> the caller's memory, while piece k crosses PCIe
+			if (rc) return rc;
+			pend_dst = dst;
+			pend_bytes = bytes;
+			pend_buf = pc.buf;
+		}
 	}
+	rc = drain();
+	if (rc) return rc;
 	QVZ_CUDA(h, cudaStreamSynchronize(h->copy_stream));
 	QVZ_CUDA(h, cudaStreamSynchronize(h->stream));
 	return QVZ_OK;
@@ -256,6 +331,7 @@ extern "C" void qvz_gpu_close(qvz_gpu *h) {
 	if (h->ev_walk_done) cudaEventDestroy(h->ev_walk_done);
 	if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
 	for (int b = 0; b < 2; ++b) {
+		if (h->pin[b]) cudaFreeHost(h->pin[b]);
 		free_dev(h->stage[b]);
 		if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
 		if (h->ev_consumed[b]) cudaEventDestroy(h->ev_consumed[b]);

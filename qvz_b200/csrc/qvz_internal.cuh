@@ -124,6 +124,8 @@ struct qvz_gpu {
 	cudaStream_t copy_stream;
 	uint8_t *stage[2];
 	size_t stage_bytes;
+	uint8_t *pin[2];         // pinned bounce buffers for pageable host memory (abi.cu)
+	size_t pin_bytes;
 	cudaEvent_t ev_copied[2], ev_consumed[2];
 	size_t Xb_cap;
 	size_t Xw_cap, cl_cap, Yw_cap, Qw_cap, Dw_cap, Ep_cap, rs_cap;
