@@ -376,6 +376,7 @@ static int settle_timings(qvz_gpu *h) {
 		h->tm.kmeans_ms = ms;
 		for (uint32_t i = 0; h->km_ev && i + 1 < h->km_ev_used; i += 2) {
 			cudaEventElapsedTime(&ms, (*h->km_ev)[i], (*h->km_ev)[i + 1]);
+			if (getenv("QVZ_DEBUG_KM")) fprintf(stderr, "[kmeans] assign launch %u: %.3f ms\n", i / 2, ms);
 			sum += ms;
 		}
 		h->tm.kmeans_assign_ms = sum;

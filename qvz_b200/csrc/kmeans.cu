@@ -16,6 +16,8 @@
 //   recenter:  mean = (uint8)(sum / count), moved_k = sum (new-old)^2 -- tiny second kernel.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "qvz_internal.cuh"
 
 // Shared-memory plan of one CTA (R = blockDim.x rows per tile):
@@ -263,6 +265,261 @@ qvz_kmeans_assign_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t 
 	if (tid < K && cnt[tid]) atomicAdd(&sums[(uint64_t) K * L.C + tid], INCR ? (unsigned long long) (long long) (int) cnt[tid] : (unsigned long long) cnt[tid]);
 }
 
+// ---- register-blocked iteration with tensor-core column sums (K <= 8) -------------------------------------------
+// The tile of 4*NT slots arrives by TMA bulk copies as above, but
+//   distances   a thread owns 4 CONSECUTIVE slots: one 16-byte shared-memory load per word column brings 4 rows, the K
+//               centroid words of the column (one or two 16-byte broadcasts) serve all 4, and the 4 x K dot products
+//               stay in registers: 1 + KP/4 LDS.128 and 4K dp4a per 16 symbols (~1.6 instructions per symbol);
+//   sums        recalculate_means' accumulator[cluster][col] += byte (src/cluster.c:96-104) is the product of a
+//               (cluster x row) coefficient matrix with the (row x column) byte matrix, and a small integer one:
+//               mma.sync.m16n8k32 (s8 x u8 -> s32, exact) does 32 rows x 8 columns per instruction.  A = +1 where the
+//               row's NEW cluster is m, and in a later iteration of a run additionally -1 where its OLD cluster is m: rows
+//               that stay put have an all-zero column and the running sums of the run only receive the rows that moved
+//               (quads of rows without a change are not even read).  B comes from the same tile: a lane reads the 4
+//               consecutive rows of one word column with one LDS.128 and turns them into four column words with 8 byte
+//               permutes (4 x 4 byte transpose), which feed 4 MMAs.  One more B column of ones counts the lines
+//               (cluster_t.count).  32-bit partials per CTA in shared memory, 64-bit global atomics at the end.
+// The counting-sort kernel above remains for K > 8.
+__device__ __forceinline__ void km_mma_s8u8(int (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+	asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+	             : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+	             : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+
+// rows (r0..r3) x bytes (columns j)  ->  T[j] = byte j of r0, r1, r2, r3
+__device__ __forceinline__ void km_transpose4(const uint4 &w, uint32_t (&T)[4]) {
+	const uint32_t t0 = __byte_perm(w.x, w.y, 0x5140), t1 = __byte_perm(w.z, w.w, 0x5140);
+	const uint32_t t2 = __byte_perm(w.x, w.y, 0x7362), t3 = __byte_perm(w.z, w.w, 0x7362);
+	T[0] = __byte_perm(t0, t1, 0x5410);
+	T[1] = __byte_perm(t0, t1, 0x7632);
+	T[2] = __byte_perm(t2, t3, 0x5410);
+	T[3] = __byte_perm(t2, t3, 0x7632);
+}
+
+static __host__ __device__ __forceinline__ uint32_t km_groups(uint32_t C4) { return (C4 + 8) / 8; }      // groups of 8 word columns incl. >= 1 padding column (the line counter)
+
+template <int KT, int NT, int RPT, bool FULL>            // NT threads walk tiles of RPT*NT slots, RPT (2 or 4) consecutive slots per thread;
+__global__ void __launch_bounds__(NT)                    // FULL = first iteration of a run (every row counts)
+qvz_kmeans_assign_mma_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t *__restrict__ cl,
+                             const uint32_t *__restrict__ means_t, const uint32_t *__restrict__ means_sq,
+                             unsigned long long *__restrict__ sums, const uint32_t *__restrict__ ctl)
+{
+	if (ctl[QVZ_CTL_DONE]) return;                       // the run has converged: this launch was enqueued speculatively (abi.cu)
+	constexpr uint32_t K = KT, KP = (KT + 3) & ~3;
+	constexpr uint32_t ROWS = RPT * NT, PITCH = ROWS + 4;    // pitch in words: tile rows stay 16-byte aligned (TMA destination)
+	constexpr uint32_t QPW = 8 * RPT, NB = RPT;          // quads of rows per warp, batches of 8 quads (= 32 rows, one MMA k-extent) per warp
+	typedef typename std::conditional<RPT == 4, uint4, uint2>::type xvec;
+	typedef typename std::conditional<RPT == 4, uint32_t, uint16_t>::type idvec;
+	extern __shared__ __align__(16) uint32_t sm[];
+	const uint32_t C4 = L.C4, G = km_groups(C4), ACCW = G * 32;     // ACCW = accumulator words per cluster (column 4*C4 = line count)
+	uint64_t *bar = (uint64_t *) sm;
+	uint32_t *tile = sm + 4;                             // [C4][PITCH]
+	uint32_t *mean4 = tile + C4 * PITCH;                 // [C4][KP]
+	uint32_t *acc = mean4 + C4 * KP;                     // [K][ACCW] signed partials
+	uint32_t *msq = acc + K * ACCW;                      // [KP]
+	uint32_t *idn = msq + KP;                            // [ROWS/4] new ids, one word per quad of rows
+	uint32_t *ido = idn + ROWS / 4;                      // [ROWS/4] old ids
+	uint32_t *qlist = ido + ROWS / 4;                    // [NT] per warp: the quads that hold a changed row, compacted
+	const uint32_t tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31u, wq = (tid >> 5) * QPW;
+	for (uint32_t i = tid; i < C4 * KP; i += NT) mean4[i] = means_t[i];      // means_t is [C4][KP], padding centroids zero
+	for (uint32_t i = tid; i < K * ACCW; i += NT) acc[i] = 0;
+	if (tid < K) msq[tid] = means_sq[tid];
+	if (tid == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(km_smem_u32(bar)));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	const uint64_t tiles = L.P / ROWS;                   // P % 4096 == 0
+	const uint32_t tile_bytes = C4 * ROWS * 4;
+	auto fetch = [&](uint64_t t) {                       // word column c4 of tile t: ROWS*4 contiguous bytes
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the tile's earlier generic reads are done (barrier before)
+		if (tid == 0) {
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(km_smem_u32(bar)), "r"(tile_bytes) : "memory");
+			const uint32_t *src = Xw + t * ROWS;
+			uint32_t dst = km_smem_u32(tile);
+			for (uint32_t c4 = 0; c4 < C4; ++c4, src += L.P, dst += PITCH * 4)
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				             ::"r"(dst), "l"(src), "r"(ROWS * 4), "r"(km_smem_u32(bar)) : "memory");
+		}
+	};
+	if (blockIdx.x < tiles) fetch(blockIdx.x);
+
+	const uint32_t m4 = (lane >> 2) * 0x01010101u;       // this lane's row of the coefficient matrix = cluster lane/4
+	const uint32_t q = lane & 3;
+	uint32_t it = 0;
+	for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+		const uint64_t p = t * ROWS + RPT * tid;         // this thread's slots
+		const uint32_t oldw = __ldg((const idvec *) (cl + p));
+		{                                                // wait for this tile's bytes
+			const uint32_t parity = it & 1, addr = km_smem_u32(bar);
+			asm volatile(
+			    "{\n"
+			    ".reg .pred p;\n"
+			    "KI_%=:\n"
+			    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+			    "@p bra KJ_%=;\n"
+			    "bra KI_%=;\n"
+			    "KJ_%=:\n"
+			    "}" ::"r"(addr), "r"(parity) : "memory");
+		}
+		uint32_t neww = oldw;
+		{
+			uint32_t D[RPT][K];
+#pragma unroll
+			for (uint32_t r = 0; r < RPT; ++r)
+#pragma unroll
+				for (uint32_t k = 0; k < K; ++k) D[r][k] = 0;
+			const xvec *tp = (const xvec *) (tile + RPT * tid);
+#pragma unroll 4
+			for (uint32_t c4 = 0; c4 < C4; ++c4) {
+				const xvec xv = tp[c4 * (PITCH / RPT)];
+				uint32_t x[RPT];
+				if constexpr (RPT == 4) { x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w; }
+				else { x[0] = xv.x; x[1] = xv.y; }
+				const uint4 *m = (const uint4 *) (mean4 + c4 * KP);
+#pragma unroll
+				for (uint32_t g = 0; g < KP / 4; ++g) {
+					const uint4 mm = m[g];
+					const uint32_t mk[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+					for (uint32_t j = 0; j < 4; ++j)
+						if (4 * g + j < K)
+#pragma unroll
+							for (uint32_t r = 0; r < RPT; ++r) D[r][4 * g + j] = __dp4a(x[r], mk[j], D[r][4 * g + j]);
+				}
+			}
+#pragma unroll
+			for (uint32_t r = 0; r < RPT; ++r) {
+				uint32_t best = 0;
+				int bestv = (int) msq[0] - 2 * (int) D[r][0];
+#pragma unroll
+				for (uint32_t k = 1; k < K; ++k) {
+					const int v = (int) msq[k] - 2 * (int) D[r][k];
+					if (v < bestv) {                     // strict '<': lowest cluster id wins ties (assign_cluster)
+						bestv = v;
+						best = k;
+					}
+				}
+				if (((oldw >> (8 * r)) & 0xFFu) != QVZ_NO_LINE) neww = (neww & ~(0xFFu << (8 * r))) | (best << (8 * r));
+			}
+		}
+		if (neww != oldw) *(idvec *) (cl + p) = (idvec) neww;
+		((idvec *) idn)[tid] = (idvec) neww;
+		((idvec *) ido)[tid] = FULL ? (idvec) 0xFFFFFFFFu : (idvec) oldw;     // first iteration: nothing to take back (0xFF matches no cluster)
+		__syncwarp();
+		// lanes < QPW stand for this warp's quads of rows: a quad contributes to the sums if one of its rows changed cluster
+		const bool mine = lane < QPW && (FULL || idn[wq + lane] != ido[wq + lane]);
+		const uint32_t qmask = __ballot_sync(0xFFFFFFFFu, mine);
+		if (mine) qlist[wbase + __popc(qmask & ((1u << lane) - 1))] = wq + lane;
+		__syncwarp();
+		const uint32_t nq = __popc(qmask), nb = (nq + 7) >> 3;        // batches of 8 quads = 32 rows
+		if (nb) {
+			// coefficient fragments and tile offsets of the batches of this warp
+			uint32_t a0[NB], a2[NB], off0[NB], off2[NB];
+#pragma unroll
+			for (uint32_t b = 0; b < NB; ++b) {
+				const uint32_t s0 = 8 * b + q, s2 = s0 + 4;
+				a0[b] = a2[b] = 0;
+				off0[b] = off2[b] = 4 * wq;
+				if (s0 < nq) {
+					const uint32_t src = qlist[wbase + s0];
+					a0[b] = __vsub4(__vcmpeq4(idn[src], m4) & 0x01010101u, __vcmpeq4(ido[src], m4) & 0x01010101u);
+					off0[b] = 4 * src;
+				}
+				if (s2 < nq) {
+					const uint32_t src = qlist[wbase + s2];
+					a2[b] = __vsub4(__vcmpeq4(idn[src], m4) & 0x01010101u, __vcmpeq4(ido[src], m4) & 0x01010101u);
+					off2[b] = 4 * src;
+				}
+			}
+			for (uint32_t g = 0; g < G; ++g) {
+				const uint32_t c4 = 8 * g + (lane >> 2);
+				int c[4][4];
+#pragma unroll
+				for (uint32_t j = 0; j < 4; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0;
+				const uint32_t *tc = tile + c4 * PITCH;
+#pragma unroll
+				for (uint32_t b = 0; b < NB; ++b) {
+					if (b < nb) {
+						uint32_t T0[4], T2[4];
+						if (c4 < C4) {
+							km_transpose4(*(const uint4 *) (tc + off0[b]), T0);
+							km_transpose4(*(const uint4 *) (tc + off2[b]), T2);
+						} else {                         // padding columns: the first one counts lines
+							T0[0] = T2[0] = c4 == C4 ? 0x01010101u : 0u;
+							T0[1] = T0[2] = T0[3] = T2[1] = T2[2] = T2[3] = 0u;
+						}
+#pragma unroll
+						for (uint32_t j = 0; j < 4; ++j) km_mma_s8u8(c[j], a0[b], a2[b], T0[j], T2[j]);
+					}
+				}
+				if ((lane >> 2) < K) {                   // rows of C = clusters; columns n = 2*(lane%4), +1 <-> word columns 8g + n
+					uint32_t *ap = acc + (lane >> 2) * ACCW + 4 * (8 * g + 2 * q);
+#pragma unroll
+					for (uint32_t j = 0; j < 4; ++j) {
+						if (c[j][0]) atomicAdd(ap + j, (uint32_t) c[j][0]);
+						if (c[j][1]) atomicAdd(ap + 4 + j, (uint32_t) c[j][1]);
+					}
+				}
+			}
+		}
+		__syncthreads();                                 // the tile has been consumed
+		if (t + gridDim.x < tiles) fetch(t + gridDim.x);
+	}
+	__syncthreads();
+	for (uint32_t i = tid; i < K * ACCW; i += NT) {      // signed partials: sign-extend (two's complement add)
+		const uint32_t k = i / ACCW, c = i - k * ACCW;
+		if (!acc[i]) continue;
+		if (c < L.C) atomicAdd(&sums[(uint64_t) k * L.C + c], (unsigned long long) (long long) (int) acc[i]);
+		else if (c == 4 * C4) atomicAdd(&sums[(uint64_t) K * L.C + k], (unsigned long long) (long long) (int) acc[i]);
+	}
+}
+
+static size_t mma_smem(uint32_t K, uint32_t C4, uint32_t rows, uint32_t NT) {
+	const uint32_t KP = (K + 3) & ~3u;
+	return (4 + (size_t) C4 * (rows + 4) + (size_t) C4 * KP + (size_t) K * km_groups(C4) * 32 + KP + rows / 2 + NT + 4) * sizeof(uint32_t);
+}
+
+template <int KT, int NT, int RPT, bool FULL>
+static void launch_mma_nt(qvz_gpu *h, int64_t *target) {
+	auto kern = qvz_kmeans_assign_mma_kernel<KT, NT, RPT, FULL>;
+	const size_t smem = mma_smem(KT, h->L.C4, RPT * NT, NT);
+	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	int per_sm = 0;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+	if (per_sm < 1) per_sm = 1;
+	if (const char *e = getenv("QVZ_KM_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;      // tuning knob
+	const uint64_t blocks = h->L.P / (RPT * NT);
+	const uint64_t cap = (uint64_t) h->sm_count * per_sm;
+	kern<<<(unsigned) (blocks < cap ? blocks : cap), NT, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_t, h->means_sq,
+	                                                                       (unsigned long long *) target, h->km_ctl);
+}
+
+// shape of a tile: QVZ_KM_SHAPE = <rows per thread><threads>, e.g. 2128 = 2 rows x 128 threads (256-slot tiles, 4 warps)
+static uint32_t mma_shape(uint32_t K, uint32_t C4) {
+	if (const char *e = getenv("QVZ_KM_SHAPE")) return (uint32_t) atoi(e);
+	return mma_smem(K, C4, 256, 128) <= 56 * 1024 ? 2128 : 264;       // long rows: 128-slot tiles
+}
+
+template <int KT, bool FULL>
+static void launch_mma_shape(qvz_gpu *h, int64_t *target) {
+	switch (mma_shape(KT, h->L.C4)) {
+	case 4128: launch_mma_nt<KT, 128, 4, FULL>(h, target); break;
+	case 464: launch_mma_nt<KT, 64, 4, FULL>(h, target); break;
+	case 432: launch_mma_nt<KT, 32, 4, FULL>(h, target); break;
+	case 2256: launch_mma_nt<KT, 256, 2, FULL>(h, target); break;
+	case 2128: launch_mma_nt<KT, 128, 2, FULL>(h, target); break;
+	default: launch_mma_nt<KT, 64, 2, FULL>(h, target); break;
+	}
+}
+
+template <int KT>
+static void launch_mma(qvz_gpu *h, int64_t *target, bool full) {
+	if (full) launch_mma_shape<KT, true>(h, target);
+	else launch_mma_shape<KT, false>(h, target);
+}
+
 // K == 1: assign_cluster has nothing to compare -- every line lands in cluster 0 -- so one iteration is just
 // recalculate_means' column sums (src/cluster.c:96-104).  Those sums are marginals of the conditional-count table
 // that calculate_statistics needs right after (sum over prev and value of (value + '!') * count), so the rows are
@@ -451,7 +708,28 @@ int qvz_kmeans_launch_assign(qvz_gpu *h, int64_t *sums_dev) {
 	// K >= 2: the first iteration of a run counts everything; later ones only move the rows that changed cluster.
 	// k1_sums doubles as the run's local running sums (the caller may all-reduce sums_dev in place).
 	const bool incr = h->k1_valid && !getenv("QVZ_KM_FULL");
-	unsigned R = 128;                                                   // measured: 128-row tiles (3-5 CTAs per SM) beat 256 and 64
+	if (K <= 8 && h->means_t && mma_smem(K, C4, 128, 64) <= 220 * 1024 && !getenv("QVZ_KM_SORTED")) {      // register-blocked, tensor-core sums (see above)
+		{
+			int64_t *target = incr ? h->k1_sums : sums_dev;                 // later iterations add signed deltas to the running sums
+			if (!incr) QVZ_CUDA(h, cudaMemsetAsync(sums_dev, 0, sum_bytes, h->stream));
+			switch (K) {
+			case 2: launch_mma<2>(h, target, !incr); break;
+			case 3: launch_mma<3>(h, target, !incr); break;
+			case 4: launch_mma<4>(h, target, !incr); break;
+			case 5: launch_mma<5>(h, target, !incr); break;
+			case 6: launch_mma<6>(h, target, !incr); break;
+			case 7: launch_mma<7>(h, target, !incr); break;
+			default: launch_mma<8>(h, target, !incr); break;
+			}
+			QVZ_LAUNCHED(h);
+			QVZ_CUDA(h, cudaGetLastError());
+			if (incr) QVZ_CUDA(h, cudaMemcpyAsync(sums_dev, h->k1_sums, sum_bytes, cudaMemcpyDeviceToDevice, h->stream));
+			else QVZ_CUDA(h, cudaMemcpyAsync(h->k1_sums, sums_dev, sum_bytes, cudaMemcpyDeviceToDevice, h->stream));
+			h->k1_valid = 1;
+			return QVZ_OK;
+		}
+	}
+	unsigned R = 128;                                                  // measured: 128-row tiles (3-5 CTAs per SM) beat 256 and 64
 	while (R > 64 && assign_smem(K, C4, R) > 110 * 1024) R >>= 1;       // keep >= 2 CTAs per SM when possible
 	if (const char *e = getenv("QVZ_KM_R")) R = (unsigned) atoi(e);     // tuning knob: 64, 128 or 256
 	const size_t smem = assign_smem(K, C4, R, incr);
