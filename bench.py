@@ -382,7 +382,8 @@ def run_native(args):
     dur_ms, alg_bytes = kern[dom]
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
     # one cluster and Q <= 41: the counting pass is the lane-private byte-plane kernel
-    names = {"kmeans_assign": "qvz_kmeans_assign_kernel", "cond_counts": "qvz_cond_counts_planes_kernel" if k == 1 else "qvz_cond_counts_kernel",
+    # (clusters <= 8: the register-blocked kernel with tensor-core column sums; more: the counting-sort kernel)
+    names = {"kmeans_assign": "qvz_kmeans_assign_mma_kernel" if k <= 8 else "qvz_kmeans_assign_kernel", "cond_counts": "qvz_cond_counts_planes_kernel" if k == 1 else "qvz_cond_counts_kernel",
              "quantize_walk": "qvz_quantize_batched_kernel"}
     step_bytes = (iters + 3) * sym_per_rank + (iters + 2) * n      # (I+3) N C + (I+2) N for I k-means iterations
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",

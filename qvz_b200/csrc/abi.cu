@@ -864,6 +864,9 @@ static int build_images(qvz_gpu *h, bool use_support) {
 	h->tab_A = rows ? A : 0;
 	h->tab_rows = rows;
 	h->tab_hrows = hrows;
+	// the hi plane holds the poison row only: every context the resident rows can reach always takes the same one of its two
+	// quantizers (qratio 0 or 128), folded into the lo plane with the ratio byte "always lo" -- no draw can change a symbol
+	h->tab_nodraw = rows && compact && hrows == 1 && !getenv("QVZ_FORCE_DRAWS");
 	h->tab_dmode = rows ? h->tab_dm : h->tab_toeplitz;
 	return QVZ_OK;
 }
@@ -937,7 +940,7 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_A], h->stream));
 	// draws first (aux stream), unless a prefetch for this seed is already in flight or done
 	const bool prefetched = h->draws_state && memcmp(h->draws_seed, well_seed, sizeof(h->draws_seed)) == 0;
-	if (!prefetched) {
+	if (!prefetched && (t || !(h->tab_A && h->tab_nodraw))) {     // (resident tables whose walk needs no draws: nothing to generate)
 		rc = start_draws(h, well_seed, t ? batched_possible(h) : h->tab_A != 0);
 		if (rc) return rc;
 	}
@@ -947,15 +950,16 @@ extern "C" int qvz_gpu_quantize(qvz_gpu *h, const struct qvz_flat_tables *t, con
 	}
 	if (h->tab_C != L.C || h->tab_K < h->K)
 		QVZ_FAIL(h, QVZ_ERR_ARG, "quantize: tables are for %u clusters x %u columns, data has %u x %u", h->tab_K, h->tab_C, h->K, L.C);
-	bool retried = false, batched = false;
+	bool retried = false, batched = false, use_draws = true;
 walk_again:
 	batched = h->tab_A != 0;
-	if (batched && h->draws_state != 2) {            // the guess said "line-major" but the tables allow the batched walk
+	use_draws = !(batched && h->tab_nodraw);         // no context mixes its quantizers: the walk reads no draws (quantize.cu)
+	if (use_draws && batched && h->draws_state != 2) {   // the guess said "line-major" but the tables allow the batched walk
 		rc = start_draws(h, well_seed, true);
 		if (rc) return rc;
 	}
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_B], h->stream));
-	QVZ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_draws, 0));      // run states (+ draws) are ready
+	if (use_draws) QVZ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_draws, 0));      // run states (+ draws) are ready
 	qvz_well_debug(h, "after run_states");
 	QVZ_CUDA(h, cudaEventRecord(h->ev[EV_F], h->stream));
 	if (batched) rc = qvz_quantize_launch_batched(h, h->tab_rows, h->tab_hrows, h->tab_A, qv_out != nullptr, h->tab_dmode);
@@ -1004,9 +1008,9 @@ walk_again:
 	// setup = everything on the main stream before the walk (table upload/composition when tables came with the call, waiting
 	// for the draws); draws = draw generator kernel on the aux stream; quantize = draws + walk kernel durations
 	float draws_ms = 0.f;
-	cudaEventElapsedTime(&draws_ms, h->ev_jump_done, h->ev_draws);      // the draw generator kernel alone (jump-ahead is setup)
+	if (use_draws && batched) cudaEventElapsedTime(&draws_ms, h->ev_jump_done, h->ev_draws);      // the draw generator kernel alone (jump-ahead is setup)
 	h->tm.quantize_setup_ms = ev_ms(h, EV_A, EV_F);
-	h->tm.quantize_draws_ms = batched ? draws_ms : 0.f;
+	h->tm.quantize_draws_ms = draws_ms;
 	h->tm.quantize_ms = h->tm.quantize_draws_ms + ev_ms(h, EV_F, EV_C);
 	h->tm.quantize_d2h_ms = ev_ms(h, EV_C, EV_D);
 	if (missing) QVZ_FAIL(h, QVZ_ERR_CONTEXT, "quantize: reached a context without a quantizer (the reference asserts, src/codebook.c:164)");

@@ -604,7 +604,10 @@ static __host__ __device__ __forceinline__ qb_geom qb_geometry(uint32_t rows, ui
 
 // DM: 0 arbitrary 72x72 matrix (global loads), 1 doubles indexed by |x-y| (-d L), 2 integers indexed by |x-y|,
 //     3 (x-y)^2 (-d M), 4 |x-y| (-d A).      S = columns staged per barrier (4, 2 or 1).
-template <int DM, bool WANT_QV, int S>
+//     DRAWS = false: no reachable context mixes its two quantizers (every qratio is 0 or 128, e.g. what -f 1.0 designs), so no
+//     draw can change a symbol: the draw stream is neither generated nor read, and the freed registers carry the row words
+//     three word columns ahead (the walk is bound by the latency of its global loads, not by their bandwidth).
+template <int DM, bool WANT_QV, int S, bool DRAWS>
 __global__ void __launch_bounds__(QB_THREADS, QB_CTAS)
 qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const uint32_t *__restrict__ Dw,
                             const uint8_t *__restrict__ cl, const uint8_t *__restrict__ G,
@@ -679,38 +682,47 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 		}
 		if (tid == 0) stage(0, gcount);
 		uint32_t xn[QB_LPT], da[QB_LPT], db[QB_LPT];     // draw words w, w+1 of the current step: da is the lower one in even steps, db in odd steps
+		                                                 // (!DRAWS: xn, da, db = the row words of word columns w, w+1, w+2 modulo 3)
 		const uint32_t *xr = Xw + pbase;                 // running pointer: one word column (P slots) per step
 		const uint32_t *drw = Dw + (uint64_t) (d0 >> 2) * L.T + (boff + tid);      // one draw word (T runs) per step
 		uint32_t *yr = Yw + pbase, *qr = WANT_QV ? Qw + pbase : nullptr;
 #pragma unroll
 		for (int j = 0; j < QB_LPT; ++j) {
 			xn[j] = ld_stream_u32(xr + j * QB_THREADS);
-			da[j] = ld_stream_u32(drw + j * QB_THREADS);
-			db[j] = ld_stream_u32(drw + L.T + j * QB_THREADS);      // Dw has spare word rows at the end (abi.cu)
+			if (DRAWS) {
+				da[j] = ld_stream_u32(drw + j * QB_THREADS);
+				db[j] = ld_stream_u32(drw + L.T + j * QB_THREADS);      // Dw has spare word rows at the end (abi.cu)
+			} else {
+				da[j] = C4 > 1 ? ld_stream_u32(xr + L.P + j * QB_THREADS) : 0u;
+				db[j] = C4 > 2 ? ld_stream_u32(xr + 2 * L.P + j * QB_THREADS) : 0u;
+			}
 		}
 		drw += 2 * (uint64_t) L.T;
+		if (!DRAWS) xr += 2 * L.P;                       // xr = the last word column that has been requested
 		// one data word (4 columns) of the QB_LPT lines of this thread; TAIL = the last, partial word
 		// ODD alternates from word to word: the draw word that was the lower one is dead after the realignment and
 		// receives the load for the next step, so no loaded value is ever copied (a copy would wait for the load)
 		auto word = [&](uint32_t c4, auto tail_tag, auto odd_tag) {
 			constexpr bool TAIL = decltype(tail_tag)::value;
-			constexpr bool ODD = decltype(odd_tag)::value;
+			constexpr int RING = decltype(odd_tag)::value;       // DRAWS: 0 / 1 = even / odd word; !DRAWS: word index modulo 3
+			constexpr bool ODD = RING == 1;
 			uint32_t (&dlo)[QB_LPT] = ODD ? db : da;
 			uint32_t (&dhi)[QB_LPT] = ODD ? da : db;
+			uint32_t (&xcur)[QB_LPT] = DRAWS ? xn : (RING == 0 ? xn : RING == 1 ? da : db);
 			uint32_t x[QB_LPT], dr[QB_LPT], t01[QB_LPT], t23[QB_LPT];
 #pragma unroll
 			for (int j = 0; j < QB_LPT; ++j) {
 				// raw ASCII bytes index the tables directly: the -33 is folded into the table base below.  A slot without
 				// a line (zero words) walks symbol 0 so that every lookup stays inside the image; nothing of it is kept.
-				x[j] = valid[j] ? xn[j] : 0x21212121u;
+				x[j] = valid[j] ? xcur[j] : 0x21212121u;
 				if (TAIL) x[j] = (x[j] & tailmask) | (0x21212121u & ~tailmask);       // columns past C count as symbol 0 (never walked)
 				// draws d0 + 4*c4 .. +3 of the run.  volatile: stays AHEAD of the loads issued below -- ptxas otherwise hoists those
 				// above it, and the shift then waits on a scoreboard shared with loads that have only just been issued
-				asm volatile("shf.r.wrap.b32 %0, %1, %2, %3;" : "=r"(dr[j]) : "r"(dlo[j]), "r"(dhi[j]), "r"(dsh));
+				if (DRAWS) asm volatile("shf.r.wrap.b32 %0, %1, %2, %3;" : "=r"(dr[j]) : "r"(dlo[j]), "r"(dhi[j]), "r"(dsh));
 				t01[j] = 0;
 				t23[j] = 0;
 			}
-			if (!TAIL) {                                 // next word's rows and draws: in flight during this word
+			if (!TAIL && DRAWS) {                        // next word's rows and draws: in flight during this word
 				xr += L.P;
 #pragma unroll
 				for (int j = 0; j < QB_LPT; ++j) {
@@ -718,6 +730,11 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 					dlo[j] = ld_stream_u32(drw + j * QB_THREADS);
 				}
 				drw += L.T;
+			}
+			if (!TAIL && !DRAWS && c4 + 3 < C4) {        // the rows of word column c4 + 3 take the place of this word's
+				xr += L.P;
+#pragma unroll
+				for (int j = 0; j < QB_LPT; ++j) xcur[j] = ld_stream_u32(xr + j * QB_THREADS);
 			}
 #pragma unroll
 			for (int g = 0; g < 4 / S; ++g) {            // the column groups (= staged images) inside this word
@@ -737,7 +754,8 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 								// draw >= qratio  <=>  (int)((qratio-1) << 24 | low bits of the previous variant) - (int)(draw << 24) < 0
 								// (exact in 32 bits: the variant is >= -2^24, the draw term <= 127 << 24), and the low 24 bits of the
 								// difference are still the variant's
-								const uint32_t d = vprev[j] - __byte_perm(dr[j], 0, 0x0444 + (b << 12));
+								// (!DRAWS: every ratio byte is 127 = "always lo", the sign of the variant itself is the answer)
+								const uint32_t d = DRAWS ? vprev[j] - __byte_perm(dr[j], 0, 0x0444 + (b << 12)) : vprev[j];
 								// byte 0 = raw data byte b of the row word, byte 1 = row byte of the previous variant,
 								// byte 2 = 0xFF if hi (sign of d, replicated), byte 3 = 0 (sign of an ASCII byte)
 								const uint32_t r = prmt_full(x[j], d, (uint32_t) (b | (5 << 4) | (0xF << 8) | ((8 | b) << 12)));
@@ -791,14 +809,33 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			}
 		};
 		uint32_t c4 = 0;
-		for (; c4 + 2 < C4; c4 += 2) {
-			word(c4, std::false_type{}, std::false_type{});
-			word(c4 + 1, std::false_type{}, std::true_type{});
+		using R0 = std::integral_constant<int, 0>;
+		using R1 = std::integral_constant<int, 1>;
+		using R2 = std::integral_constant<int, 2>;
+		if (DRAWS) {
+			for (; c4 + 2 < C4; c4 += 2) {
+				word(c4, std::false_type{}, R0{});
+				word(c4 + 1, std::false_type{}, R1{});
+			}
+			if (c4 + 1 < C4) {
+				word(c4, std::false_type{}, R0{});
+				word(c4 + 1, std::true_type{}, R1{});
+			} else word(c4, std::true_type{}, R0{});
+		} else {
+			for (; c4 + 3 < C4; c4 += 3) {
+				word(c4, std::false_type{}, R0{});
+				word(c4 + 1, std::false_type{}, R1{});
+				word(c4 + 2, std::false_type{}, R2{});
+			}
+			if (c4 + 2 < C4) {
+				word(c4, std::false_type{}, R0{});
+				word(c4 + 1, std::false_type{}, R1{});
+				word(c4 + 2, std::true_type{}, R2{});
+			} else if (c4 + 1 < C4) {
+				word(c4, std::false_type{}, R0{});
+				word(c4 + 1, std::true_type{}, R1{});
+			} else word(c4, std::true_type{}, R0{});
 		}
-		if (c4 + 1 < C4) {
-			word(c4, std::false_type{}, std::false_type{});
-			word(c4 + 1, std::true_type{}, std::true_type{});
-		} else word(c4, std::true_type{}, std::false_type{});
 #pragma unroll
 		for (int j = 0; j < QB_LPT; ++j) {
 			// a line that met a context without a quantizer sits in the poison row (row byte 0) after its last column
@@ -864,9 +901,9 @@ int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, uint32_
 	return QVZ_OK;
 }
 
-template <int DM, bool WANT_QV, int S>
-static void launch_batched(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_t A) {
-	auto kern = qvz_quantize_batched_kernel<DM, WANT_QV, S>;
+template <int DM, bool WANT_QV, int S, bool DRAWS>
+static void launch_batched_d(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_t A) {
+	auto kern = qvz_quantize_batched_kernel<DM, WANT_QV, S, DRAWS>;
 	const size_t smem = batched_smem(rows, hrows, A, S);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	const uint64_t nbatch = (uint64_t) (h->L.T / QB_LINES) * h->L.Lr;     // T % QB_LINES == 0 (QVZ_RUN_ALIGN)
@@ -874,6 +911,12 @@ static void launch_batched(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_t A
 	const unsigned grid = (unsigned) (nbatch < resident ? nbatch : resident);
 	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->G, h->start, h->D, rows, hrows, A, h->Yw,
 	                                            WANT_QV ? h->Qw : nullptr, h->Ep, h->flags);
+}
+
+template <int DM, bool WANT_QV, int S>
+static void launch_batched(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_t A) {
+	if (h->tab_nodraw) launch_batched_d<DM, WANT_QV, S, false>(h, rows, hrows, A);
+	else launch_batched_d<DM, WANT_QV, S, true>(h, rows, hrows, A);
 }
 
 template <int DM, bool WANT_QV>
@@ -897,7 +940,7 @@ static void launch_batched_dm(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_
 // dm: see the kernel
 int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_t A, int want_qv, int dm) {
 	const uint32_t S = qvz_quantize_batched_group(rows, hrows, A);
-	if (getenv("QVZ_DEBUG_WALK")) fprintf(stderr, "[walk] rows %u hi rows %u A %u S %u smem %zu dm %d\n", rows, hrows, A, S, batched_smem(rows, hrows, A, S), dm);
+	if (getenv("QVZ_DEBUG_WALK")) fprintf(stderr, "[walk] rows %u hi rows %u A %u S %u smem %zu dm %d draws %d\n", rows, hrows, A, S, batched_smem(rows, hrows, A, S), dm, !h->tab_nodraw);
 	if (want_qv) launch_batched_dm<true>(h, rows, hrows, A, S, dm);
 	else launch_batched_dm<false>(h, rows, hrows, A, S, dm);
 	QVZ_LAUNCHED(h);

@@ -134,6 +134,7 @@ struct qvz_gpu {
 	uint32_t tab_K, tab_C, tab_A, tab_rows, tab_hrows;    // tab_A = 0: the line-major walk (W / R only)
 	uint32_t tab_box;                // alphabet box of the images: > every symbol of the rows and every value a quantizer can emit for one
 	int tab_dmode, tab_valid, tab_toeplitz, tab_dm, tab_support_used;
+	int tab_nodraw;                  // no reachable context mixes its two quantizers: the walk needs no draws (quantize.cu)
 
 	// events / timings: recorded without synchronising, turned into milliseconds by qvz_gpu_get_timings
 	cudaEvent_t ev[8];
