@@ -6,10 +6,11 @@ from oracle.bindings import FlatTables
 ALPHABET = 72
 
 
-def synthetic_tables(K: int, C: int, seed: int = 0, nsym: int = 42, dist: str = "L") -> FlatTables:
+def synthetic_tables(K: int, C: int, seed: int = 0, nsym: int = 42, dist: str = "L", mixing: bool = True) -> FlatTables:
     """Valid `struct qvz_flat_tables` without running the (slow) codebook design: every column has
     all 72 values as contexts (so no context can be missing), each context gets a coarse (lo) and a
-    finer (hi) staircase quantizer with random steps/offsets and a random mixing ratio in [0,128]."""
+    finer (hi) staircase quantizer with random steps/offsets and a random mixing ratio in [0,128]
+    (mixing=False: only the ratios 0 and 128 -- no WELL draw can change a symbol)."""
     rng = np.random.default_rng(seed)
     KC = K * C
     nctx = np.full(KC, ALPHABET, np.uint32)
@@ -23,6 +24,8 @@ def synthetic_tables(K: int, C: int, seed: int = 0, nsym: int = 42, dist: str = 
     q_off[1:] = np.cumsum(2 * nctx.astype(np.uint64))[:-1]
     nq = int(2 * nctx.sum())
     qratio = rng.integers(0, 129, nq // 2, dtype=np.uint8)
+    if not mixing:                                 # every context always takes the same one of its two quantizers (what -f 1.0 designs)
+        qratio = np.where(rng.integers(0, 2, nq // 2) == 1, 128, 0).astype(np.uint8)
     x = np.arange(ALPHABET)
     step = rng.integers(1, 9, nq)
     step[1::2] = np.maximum(1, step[0::2] - rng.integers(0, 3, nq // 2))      # hi is at least as fine as lo

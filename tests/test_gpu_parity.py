@@ -95,6 +95,54 @@ def test_kmeans_and_counts_vs_oracle(gpu, oracle, n, c, k, thr):
     assert np.array_equal(gpu.cond_counts(), oracle.cond_counts(rows, c, k, o["ids"]))
 
 
+@pytest.mark.parametrize("shape", ["2128", "264", "2256", "464", "432", "sorted"])
+@pytest.mark.parametrize("n,c,k", [(70_000, 150, 5), (40_000, 250, 2), (33_333, 101, 8), (9000, 30, 3)])
+def test_kmeans_kernel_variants(gpu, oracle, n, c, k, shape):
+    """Every tile shape of the register-blocked k-means kernel (rows per thread x threads: tensor-core column sums,
+    full and incremental iterations) and the counting-sort kernel give the oracle's ids, means, `moved` log and counts."""
+    import os
+    rows = synth_rows(n, c, seed=77 + n).numpy()
+    picks = kmeans_init_lines(n, k, GLIBC_RAND)
+    init = rows[picks, :c]
+    o = oracle.kmeans(rows, c, init, 4.0)
+    assert o["iters"] >= 2                         # an incremental iteration has run
+    _load(gpu, rows, c)
+    key, val = ("QVZ_KM_SORTED", "1") if shape == "sorted" else ("QVZ_KM_SHAPE", shape)
+    os.environ[key] = val
+    try:
+        r = gpu.kmeans(init, 4.0)
+    finally:
+        del os.environ[key]
+    assert r["iters"] == o["iters"]
+    for name in ("ids", "means", "counts", "moved"):
+        assert np.array_equal(r[name], o[name]), name
+
+
+@pytest.mark.parametrize("n,c,k,dist", [(50_000, 150, 5, "M"), (12_345, 250, 2, "A"), (8000, 101, 1, "L"), (5, 3, 2, "M")])
+def test_quantize_without_draws(gpu, oracle, n, c, k, dist):
+    """Tables in which no context mixes its two quantizers (qratio 0 or 128 only): the walk neither generates nor reads
+    the draw stream, and gives the oracle's bytes all the same; so does the same walk forced to read the draws."""
+    import os
+    rows = synth_rows(n, c, seed=3000 + n).numpy()
+    ids = np.random.default_rng(n).integers(0, k, n, dtype=np.uint8)
+    t = synthetic_tables(k, c, seed=n, dist=dist, mixing=False)
+    seed = np.random.default_rng(c).integers(0, 2**31, 32, dtype=np.uint32)
+    _load(gpu, rows, c)
+    gpu.set_clusters(k, ids)
+    o = oracle.quantize(rows, c, ids, t, seed)
+    q = _quantize_both_paths(gpu, t, seed)
+    assert gpu.timings()["quantize_draws_ms"] >= 0.0
+    os.environ["QVZ_FORCE_DRAWS"] = "1"
+    try:
+        q2 = gpu.quantize(t, seed, want_qv=True, want_err=True)
+    finally:
+        del os.environ["QVZ_FORCE_DRAWS"]
+    for res in (q, q2):
+        assert np.array_equal(res["symbols"], o["symbols"])
+        assert np.array_equal(res["qv"], o["qv"])
+        assert np.array_equal(res["line_err"], o["line_err"])
+
+
 @pytest.mark.parametrize("n,c,k,dist", [(60_000, 150, 3, "L"), (20_000, 101, 1, "M"), (7777, 250, 5, "A"), (6, 3, 2, "L")])
 def test_quantize_vs_oracle_synthetic_tables(gpu, oracle, n, c, k, dist):
     rows = synth_rows(n, c, seed=2000 + n).numpy()
