@@ -326,6 +326,7 @@ int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int dmode) {
 #define QB_LPT 4
 #define QB_LINES (QB_THREADS * QB_LPT)
 static_assert(QVZ_RUN_ALIGN % QB_LINES == 0, "a step (T slots) must be a whole number of walk batches");
+#define QB_MAX_BUF 8                    // buffers of the table-image ring
 #define QB_POISON_ENTRY 0x007F0000u     // qv 0, next row 0, state byte 0x7F (no quantizer has 127 states), ratio byte 0
 #define QB_MAX_ROWS 255u                // the row index travels in one byte
 #define QB_MAX_A 62u                    // 4*A must fit the dp4a coefficient byte
@@ -613,10 +614,12 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
                             const uint8_t *__restrict__ cl, const uint8_t *__restrict__ G,
                             const uint32_t *__restrict__ start, const double *__restrict__ D, uint32_t rows,
                             uint32_t hrows, uint32_t A, uint32_t *__restrict__ Yw, uint32_t *__restrict__ Qw,
-                            double *__restrict__ Ep, int *__restrict__ flags)
+                            double *__restrict__ Ep, int *__restrict__ flags, uint32_t nbuf)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
-	// [dd: 72 doubles (or 72 words)][4 mbarriers][buffer 0][buffer 1]; a buffer = S consecutive column images of G
+	// [dd: 72 doubles (or 72 words)][2 x 8 mbarriers][buffer 0] .. [buffer nbuf-1]; a buffer = S consecutive column images of G,
+	// the buffers form a ring: the images of the column groups are requested nbuf-1 groups ahead of their use (the sequence
+	// of column groups simply repeats batch after batch, so the ring runs across batch boundaries).
 	// full[b]: the image has landed (TMA transaction count); empty[b]: every warp is done reading it (one arrival per warp).
 	// There is no CTA-wide barrier in the walk: a warp only waits for the image it needs, and the one thread that issues
 	// the copies waits for the buffer it is about to overwrite.
@@ -624,36 +627,51 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 	double *dd = (double *) smem;
 	uint32_t *di = smem;
 	uint64_t *full = (uint64_t *) (smem + DD_WORDS);
-	uint64_t *empty = full + 2;
+	uint64_t *empty = full + QB_MAX_BUF;
 	const uint32_t A4 = A * 4;
 	const qb_geom geo = qb_geometry(rows, hrows, A);
 	const uint32_t col_bytes = geo.col_bytes;
 	const uint32_t buf_bytes = S * col_bytes;
-	const uint32_t buf0 = smem_u32(smem + DD_WORDS + 8);
+	volatile uint32_t *ps = smem + DD_WORDS + 4 * QB_MAX_BUF;     // producer state (thread 0 only; kept out of the registers of the walk)
+	const uint32_t buf0 = smem_u32(smem + DD_WORDS + 4 * QB_MAX_BUF + 4);
 	const uint32_t dd_addr = smem_u32(smem);
 	const uint32_t tid = threadIdx.x;
 	if (DM == 1 && tid < QVZ_ALPHABET) dd[tid] = D[tid];
 	if (DM == 2 && tid < QVZ_ALPHABET) di[tid] = (uint32_t) D[tid];
 	if (tid == 0) {
-		mbar_init(&full[0], 1);
-		mbar_init(&full[1], 1);
-		mbar_init(&empty[0], QB_THREADS / 32);
-		mbar_init(&empty[1], QB_THREADS / 32);
+		for (uint32_t b = 0; b < nbuf; ++b) {
+			mbar_init(&full[b], 1);
+			mbar_init(&empty[b], QB_THREADS / 32);
+		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
 	const uint32_t C = L.C, C4 = L.C4;
 	const uint32_t coef = 4u | (A4 << 8) | (geo.c2 << 16);   // dp4a: 4 * data byte + 4A * row byte + c * (hi ? 255 : 0)
-	uint32_t gcount = 0;                             // column groups consumed so far (uniform): buffer = gcount & 1
-	auto stage = [&](uint32_t col0, uint32_t g) {    // thread 0: columns col0 .. min(col0+S, C)-1 -> buffer g & 1 (its g>>1-th fill)
-		const uint32_t ncol = (C - col0 < (uint32_t) S) ? C - col0 : (uint32_t) S;
+	// consumer side (uniform): buffer and phase parity of the column group being walked
+	uint32_t cb = 0, cph = 0;
+	// producer side (thread 0): ps[0] next buffer to fill, ps[1] how often it has been filled, ps[2] next column group, ps[3] groups left
+	auto stage_next = [&]() {                        // thread 0: the next column group of the sequence -> the next buffer of the ring
+		const uint32_t pleft = ps[3];
+		if (!pleft) return;
+		uint32_t pb = ps[0], pf = ps[1];
+		const uint32_t pcol = ps[2];
+		const uint32_t ncol = (C - pcol < (uint32_t) S) ? C - pcol : (uint32_t) S;
 		const uint32_t bytes = ncol * col_bytes;
-		if (g >= 2) mbar_wait(&empty[g & 1], ((g >> 1) - 1) & 1);      // every warp has finished the buffer's previous image
+		if (pf) mbar_wait(&empty[pb], (pf - 1) & 1);                   // every warp has finished the buffer's previous image
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... and those generic reads are ordered before the async write
-		mbar_expect_tx(&full[g & 1], bytes);
+		mbar_expect_tx(&full[pb], bytes);
 		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-		             ::"r"(buf0 + (g & 1) * buf_bytes), "l"(G + (uint64_t) col0 * col_bytes), "r"(bytes), "r"(smem_u32(&full[g & 1])) : "memory");
+		             ::"r"(buf0 + pb * buf_bytes), "l"(G + (uint64_t) pcol * col_bytes), "r"(bytes), "r"(smem_u32(&full[pb])) : "memory");
+		ps[2] = pcol + S < C ? pcol + S : 0;
+		if (++pb == nbuf) {
+			pb = 0;
+			pf += 1;
+		}
+		ps[0] = pb;
+		ps[1] = pf;
+		ps[3] = pleft - 1;
 	};
 
 	bool missing = false;
@@ -662,6 +680,11 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 	const uint32_t bps = L.T / QB_LINES;                 // batches per step
 	const uint64_t nbatch = (uint64_t) bps * L.Lr;
 	const uint32_t tailmask = (C & 3) ? (0xFFFFFFFFu >> (8 * (4 - (C & 3)))) : 0xFFFFFFFFu;     // live bytes of the last word
+	if (tid == 0 && blockIdx.x < nbatch) {
+		ps[0] = ps[1] = ps[2] = 0;
+		ps[3] = (uint32_t) ((nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x) * ((C + S - 1) / S);
+		for (uint32_t b = 0; b + 1 < nbuf; ++b) stage_next();
+	}
 	for (uint64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
 		const uint32_t step = (uint32_t) (batch / bps), boff = (uint32_t) (batch - (uint64_t) step * bps) * QB_LINES;
 		const uint64_t pbase = (uint64_t) step * L.T + boff + tid;
@@ -680,7 +703,6 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			erri[j] = 0;
 			errd[j] = 0.0;                               // 0.0 + d == d exactly: same bits as "error = d" at column 0
 		}
-		if (tid == 0) stage(0, gcount);
 		uint32_t xn[QB_LPT], da[QB_LPT], db[QB_LPT];     // draw words w, w+1 of the current step: da is the lower one in even steps, db in odd steps
 		                                                 // (!DRAWS: xn, da, db = the row words of word columns w, w+1, w+2 modulo 3)
 		const uint32_t *xr = Xw + pbase;                 // running pointer: one word column (P slots) per step
@@ -740,10 +762,9 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 			for (int g = 0; g < 4 / S; ++g) {            // the column groups (= staged images) inside this word
 				const uint32_t col0 = 4 * c4 + g * S;
 				if (!TAIL || col0 < C) {
-					if (tid == 0 && col0 + S < C) stage(col0 + S, gcount + 1);
-					mbar_wait(&full[gcount & 1], (gcount >> 1) & 1);   // this group's image has landed
-					const uint32_t tabg = buf0 + (gcount & 1) * buf_bytes;
-					gcount += 1;
+					if (tid == 0) stage_next();          // the group nbuf-1 ahead of this one
+					mbar_wait(&full[cb], cph);           // this group's image has landed
+					const uint32_t tabg = buf0 + cb * buf_bytes;
 #pragma unroll
 					for (int sidx = 0; sidx < S; ++sidx) {
 						const int b = g * S + sidx;
@@ -769,7 +790,11 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 						}
 					}
 					__syncwarp();                        // this warp is done with the group's image
-					if ((tid & 31) == 0) mbar_arrive(&empty[(gcount - 1) & 1]);
+					if ((tid & 31) == 0) mbar_arrive(&empty[cb]);
+					if (++cb == nbuf) {
+						cb = 0;
+						cph ^= 1;
+					}
 				}
 			}
 			uint32_t qvw[QB_LPT];
@@ -848,8 +873,18 @@ qvz_quantize_batched_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, const
 	if (missing) atomicOr(&flags[2], 1);
 }
 
-static size_t batched_smem(uint32_t rows, uint32_t hrows, uint32_t A, uint32_t S) {
-	return 2 * (QVZ_ALPHABET + 2) * sizeof(uint32_t) + 32 + 2 * (size_t) S * qb_geometry(rows, hrows, A).col_bytes;
+static size_t batched_smem(uint32_t rows, uint32_t hrows, uint32_t A, uint32_t S, uint32_t nbuf = 2) {
+	return 2 * (QVZ_ALPHABET + 2) * sizeof(uint32_t) + 16 * QB_MAX_BUF + 16 + (size_t) nbuf * S * qb_geometry(rows, hrows, A).col_bytes;
+}
+
+// buffers of the ring: 2 (measured on cfg2, where more fit: 3 buffers 2.38 TB/s, 2 buffers 2.42; on cfg4 four buffers of 2
+// columns 2.98 TB/s against 3.12 for two of 4 columns: the size of a group matters, the depth of the ring does not);
+// QVZ_WALK_NBUF = up to as many as fit
+static uint32_t batched_nbuf(uint32_t rows, uint32_t hrows, uint32_t A, uint32_t S) {
+	uint32_t fit = 2, n = 2;
+	while (fit < QB_MAX_BUF && batched_smem(rows, hrows, A, S, fit + 1) <= (QB_CTAS == 1 ? 226 : 112) * 1024) ++fit;
+	if (const char *e = getenv("QVZ_WALK_NBUF")) n = (uint32_t) atoi(e) >= 2 && (uint32_t) atoi(e) <= fit ? (uint32_t) atoi(e) : n;
+	return n;
 }
 
 size_t qvz_quantize_image_bytes(uint32_t C, uint32_t rows, uint32_t hrows, uint32_t A) { return (size_t) C * qb_geometry(rows, hrows, A).col_bytes; }
@@ -857,7 +892,9 @@ size_t qvz_quantize_image_bytes(uint32_t C, uint32_t rows, uint32_t hrows, uint3
 // columns staged per barrier: the largest of 4, 2, 1 whose double buffer fits; 0 = batched path unusable
 uint32_t qvz_quantize_batched_group(uint32_t rows, uint32_t hrows, uint32_t A) {
 	if (A > QB_MAX_A || rows > QB_MAX_ROWS + 1) return 0;
-	for (uint32_t S = 4; S >= 1; S >>= 1)
+	uint32_t smax = 4;
+	if (const char *e = getenv("QVZ_WALK_S")) smax = atoi(e) == 1 ? 1 : atoi(e) == 2 ? 2 : 4;      // tuning knob
+	for (uint32_t S = smax; S >= 1; S >>= 1)
 		if (batched_smem(rows, hrows, A, S) <= (QB_CTAS == 1 ? 226 : 112) * 1024) return S;       // 227 KB per CTA on sm_100
 	return 0;
 }
@@ -906,13 +943,14 @@ int qvz_quantize_compact(qvz_gpu *h, uint32_t K, uint32_t C, uint32_t A, uint32_
 template <int DM, bool WANT_QV, int S, bool DRAWS>
 static void launch_batched_d(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_t A) {
 	auto kern = qvz_quantize_batched_kernel<DM, WANT_QV, S, DRAWS>;
-	const size_t smem = batched_smem(rows, hrows, A, S);
+	const uint32_t nbuf = batched_nbuf(rows, hrows, A, S);
+	const size_t smem = batched_smem(rows, hrows, A, S, nbuf);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	const uint64_t nbatch = (uint64_t) (h->L.T / QB_LINES) * h->L.Lr;     // T % QB_LINES == 0 (QVZ_RUN_ALIGN)
 	const uint64_t resident = (uint64_t) h->sm_count * QB_CTAS;
 	const unsigned grid = (unsigned) (nbatch < resident ? nbatch : resident);
 	kern<<<grid, QB_THREADS, smem, h->stream>>>(h->L, h->Xw, h->Dw, h->cl, h->G, h->start, h->D, rows, hrows, A, h->Yw,
-	                                            WANT_QV ? h->Qw : nullptr, h->Ep, h->flags);
+	                                            WANT_QV ? h->Qw : nullptr, h->Ep, h->flags, nbuf);
 }
 
 template <int DM, bool WANT_QV, int S>
@@ -942,7 +980,7 @@ static void launch_batched_dm(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_
 // dm: see the kernel
 int qvz_quantize_launch_batched(qvz_gpu *h, uint32_t rows, uint32_t hrows, uint32_t A, int want_qv, int dm) {
 	const uint32_t S = qvz_quantize_batched_group(rows, hrows, A);
-	if (getenv("QVZ_DEBUG_WALK")) fprintf(stderr, "[walk] rows %u hi rows %u A %u S %u smem %zu dm %d draws %d\n", rows, hrows, A, S, batched_smem(rows, hrows, A, S), dm, !h->tab_nodraw);
+	if (getenv("QVZ_DEBUG_WALK")) fprintf(stderr, "[walk] rows %u hi rows %u A %u S %u ring %u smem %zu dm %d draws %d\n", rows, hrows, A, S, batched_nbuf(rows, hrows, A, S), batched_smem(rows, hrows, A, S, batched_nbuf(rows, hrows, A, S)), dm, !h->tab_nodraw);
 	if (want_qv) launch_batched_dm<true>(h, rows, hrows, A, S, dm);
 	else launch_batched_dm<false>(h, rows, hrows, A, S, dm);
 	QVZ_LAUNCHED(h);
