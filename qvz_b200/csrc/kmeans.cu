@@ -298,8 +298,8 @@ __device__ __forceinline__ void km_transpose4(const uint4 &w, uint32_t (&T)[4]) 
 
 static __host__ __device__ __forceinline__ uint32_t km_groups(uint32_t C4) { return (C4 + 8) / 8; }      // groups of 8 word columns incl. >= 1 padding column (the line counter)
 
-template <int KT, int NT, int RPT, bool FULL>            // NT threads walk tiles of RPT*NT slots, RPT (2 or 4) consecutive slots per thread;
-__global__ void __launch_bounds__(NT)                    // FULL = first iteration of a run (every row counts)
+template <int KT, int NT, int RPT, bool FULL, int NBUF>  // NT threads walk tiles of RPT*NT slots, RPT (2 or 4) consecutive slots per thread;
+__global__ void __launch_bounds__(NT)                    // FULL = first iteration of a run (every row counts); NBUF tile buffers (1 or 2)
 qvz_kmeans_assign_mma_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint8_t *__restrict__ cl,
                              const uint32_t *__restrict__ means_t, const uint32_t *__restrict__ means_sq,
                              unsigned long long *__restrict__ sums, const uint32_t *__restrict__ ctl)
@@ -308,51 +308,63 @@ qvz_kmeans_assign_mma_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint
 	constexpr uint32_t K = KT, KP = (KT + 3) & ~3;
 	constexpr uint32_t ROWS = RPT * NT, PITCH = ROWS + 4;    // pitch in words: tile rows stay 16-byte aligned (TMA destination)
 	constexpr uint32_t QPW = 8 * RPT, NB = RPT;          // quads of rows per warp, batches of 8 quads per warp
-	typedef typename std::conditional<RPT == 4, uint4, uint2>::type xvec;
-	typedef typename std::conditional<RPT == 4, uint32_t, uint16_t>::type idvec;
+	typedef typename std::conditional<RPT == 4, uint4, typename std::conditional<RPT == 2, uint2, uint32_t>::type>::type xvec;
+	typedef typename std::conditional<RPT == 4, uint32_t, typename std::conditional<RPT == 2, uint16_t, uint8_t>::type>::type idvec;
 	extern __shared__ __align__(16) uint32_t sm[];
 	const uint32_t C4 = L.C4, G = km_groups(C4), ACCW = G * 32;     // ACCW = accumulator words per cluster (column 4*C4 = line count)
-	uint64_t *bar = (uint64_t *) sm;
-	uint32_t *tile = sm + 4;                             // [C4][PITCH]
-	uint32_t *mean4 = tile + C4 * PITCH;                 // [C4][KP]
+	uint64_t *bar = (uint64_t *) sm;                     // [NBUF]
+	uint32_t *tile0 = sm + 4;                            // [NBUF][C4][PITCH]: with two buffers the next tile lands while this one is worked on
+	uint32_t *mean4 = tile0 + NBUF * C4 * PITCH;         // [C4][KP]
 	uint32_t *acc = mean4 + C4 * KP;                     // [K][ACCW] signed partials
 	uint32_t *msq = acc + K * ACCW;                      // [KP]
-	uint32_t *idn = msq + KP;                            // [ROWS/4] new ids, one word per quad of rows
-	uint32_t *ido = idn + ROWS / 4;                      // [ROWS/4] old ids
-	uint32_t *qlist = ido + ROWS / 4;                    // [ROWS/4] per warp: its quads that hold a changed row, compacted
+	uint16_t *idn = (uint16_t *) (msq + KP);             // [ROWS/4] new ids of a quad of rows, one NIBBLE per row (0xF = no line)
+	uint16_t *ido = (uint16_t *) (msq + KP + ROWS / 4);  // [ROWS/4] old ids
+	uint32_t *qlist = msq + KP + 2 * (ROWS / 4);          // [ROWS/4] per warp: its quads that hold a changed row, compacted
 	const uint32_t tid = threadIdx.x, lane = tid & 31, wq = (tid >> 5) * QPW;
 	for (uint32_t i = tid; i < C4 * KP; i += NT) mean4[i] = means_t[i];      // means_t is [C4][KP], padding centroids zero
 	for (uint32_t i = tid; i < K * ACCW; i += NT) acc[i] = 0;
 	if (tid < K) msq[tid] = means_sq[tid];
 	if (tid == 0) {
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(km_smem_u32(bar)));
+		for (uint32_t b = 0; b < NBUF; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(km_smem_u32(bar + b)));
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
 	const uint64_t tiles = L.P / ROWS;                   // P % 4096 == 0
 	const uint32_t tile_bytes = C4 * ROWS * 4;
-	auto fetch = [&](uint64_t t) {                       // word column c4 of tile t: ROWS*4 contiguous bytes
-		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the tile's earlier generic reads are done (barrier before)
+	auto fetch = [&](uint64_t t, uint32_t b) {           // word column c4 of tile t: ROWS*4 contiguous bytes -> buffer b
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the buffer's earlier generic reads are done (barrier before)
 		if (tid == 0) {
-			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(km_smem_u32(bar)), "r"(tile_bytes) : "memory");
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(km_smem_u32(bar + b)), "r"(tile_bytes) : "memory");
 			const uint32_t *src = Xw + t * ROWS;
-			uint32_t dst = km_smem_u32(tile);
+			uint32_t dst = km_smem_u32(tile0 + b * C4 * PITCH);
 			for (uint32_t c4 = 0; c4 < C4; ++c4, src += L.P, dst += PITCH * 4)
 				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-				             ::"r"(dst), "l"(src), "r"(ROWS * 4), "r"(km_smem_u32(bar)) : "memory");
+				             ::"r"(dst), "l"(src), "r"(ROWS * 4), "r"(km_smem_u32(bar + b)) : "memory");
 		}
 	};
-	if (blockIdx.x < tiles) fetch(blockIdx.x);
+	for (uint32_t b = 0; b < NBUF; ++b)
+		if (blockIdx.x + (uint64_t) b * gridDim.x < tiles) fetch(blockIdx.x + (uint64_t) b * gridDim.x, b);
 
-	const uint32_t m4 = (lane >> 2) * 0x01010101u;       // this lane's row of the coefficient matrix = cluster lane/4
+	// this lane's row of the coefficient matrix = cluster m = lane/4: byte j of the pair (oh_lo, oh_hi) is 1 iff j == m, so one
+	// byte permute with the 4 id nibbles of a quad as selector gives its 4 coefficients (nibble 0xF replicates the sign of
+	// byte 7, i.e. 0: a slot without a line, or the "old" side of the first iteration, belongs to no cluster)
+	const uint32_t oh_lo = (lane >> 2) < 4 ? 1u << (8 * (lane >> 2)) : 0u, oh_hi = (lane >> 2) >= 4 ? 1u << (8 * ((lane >> 2) - 4)) : 0u;
+	auto coef4 = [&](uint32_t quad) {                    // (+1 new cluster, -1 old cluster) per row of the quad, as 4 signed bytes
+		uint32_t en, eo;
+		asm("prmt.b32 %0, %1, %2, %3;" : "=r"(en) : "r"(oh_lo), "r"(oh_hi), "r"((uint32_t) idn[quad]));
+		asm("prmt.b32 %0, %1, %2, %3;" : "=r"(eo) : "r"(oh_lo), "r"(oh_hi), "r"((uint32_t) ido[quad]));
+		return ((en | 0x80808080u) - eo) ^ 0x80808080u;  // per-byte en - eo: no borrow can cross a byte
+	};
 	const uint32_t q = lane & 3;
 	uint32_t it = 0;
 	for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
 		const uint64_t p = t * ROWS + RPT * tid;         // this thread's slots
 		const uint32_t oldw = __ldg((const idvec *) (cl + p));
+		const uint32_t buf = NBUF == 2 ? (it & 1) : 0;
+		const uint32_t *tile = tile0 + buf * C4 * PITCH;
 		{                                                // wait for this tile's bytes
-			const uint32_t parity = it & 1, addr = km_smem_u32(bar);
+			const uint32_t parity = (NBUF == 2 ? (it >> 1) : it) & 1, addr = km_smem_u32(bar + buf);
 			asm volatile(
 			    "{\n"
 			    ".reg .pred p;\n"
@@ -376,7 +388,8 @@ qvz_kmeans_assign_mma_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint
 				const xvec xv = tp[c4 * (PITCH / RPT)];
 				uint32_t x[RPT];
 				if constexpr (RPT == 4) { x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w; }
-				else { x[0] = xv.x; x[1] = xv.y; }
+				else if constexpr (RPT == 2) { x[0] = xv.x; x[1] = xv.y; }
+				else x[0] = xv;
 				const uint4 *m = (const uint4 *) (mean4 + c4 * KP);
 #pragma unroll
 				for (uint32_t g = 0; g < KP / 4; ++g) {
@@ -405,8 +418,24 @@ qvz_kmeans_assign_mma_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint
 			}
 		}
 		if (neww != oldw) *(idvec *) (cl + p) = (idvec) neww;
-		((idvec *) idn)[tid] = (idvec) neww;
-		((idvec *) ido)[tid] = FULL ? (idvec) 0xFFFFFFFFu : (idvec) oldw;     // first iteration: nothing to take back (0xFF matches no cluster)
+		// ids -> nibbles: byte r of neww / oldw -> nibble r of this thread's part of the quad
+		if constexpr (RPT == 4) {
+			idn[tid] = (uint16_t) ((neww & 0xFu) | ((neww >> 4) & 0xF0u) | ((neww >> 8) & 0xF00u) | ((neww >> 12) & 0xF000u));
+			ido[tid] = FULL ? (uint16_t) 0xFFFFu : (uint16_t) ((oldw & 0xFu) | ((oldw >> 4) & 0xF0u) | ((oldw >> 8) & 0xF00u) | ((oldw >> 12) & 0xF000u));
+		} else if constexpr (RPT == 2) {
+			((uint8_t *) idn)[tid] = (uint8_t) ((neww & 0xFu) | ((neww >> 4) & 0xF0u));
+			((uint8_t *) ido)[tid] = FULL ? (uint8_t) 0xFFu : (uint8_t) ((oldw & 0xFu) | ((oldw >> 4) & 0xF0u));     // first iteration: nothing to take back
+		} else {                                         // one row per thread: the 4 lanes of a quad put their nibbles together
+			uint32_t vn = (neww & 0xFu) << (4 * (lane & 3)), vo = (FULL ? 0xFu : (oldw & 0xFu)) << (4 * (lane & 3));
+			vn |= __shfl_xor_sync(0xFFFFFFFFu, vn, 1);
+			vo |= __shfl_xor_sync(0xFFFFFFFFu, vo, 1);
+			vn |= __shfl_xor_sync(0xFFFFFFFFu, vn, 2);
+			vo |= __shfl_xor_sync(0xFFFFFFFFu, vo, 2);
+			if ((lane & 3) == 0) {
+				idn[tid >> 2] = (uint16_t) vn;
+				ido[tid >> 2] = (uint16_t) vo;
+			}
+		}
 		__syncwarp();
 		// lanes < QPW stand for this warp's quads of rows: a quad contributes to the sums if one of its rows changed cluster
 		// (measured alternatives: pooling the quads of all warps of the CTA so that late iterations run fewer, fuller batches
@@ -426,12 +455,12 @@ qvz_kmeans_assign_mma_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint
 				off0[b] = off2[b] = 4 * wq;
 				if (s0 < nq) {
 					const uint32_t src = qlist[wq + s0];
-					a0[b] = __vsub4(__vcmpeq4(idn[src], m4) & 0x01010101u, __vcmpeq4(ido[src], m4) & 0x01010101u);
+					a0[b] = coef4(src);
 					off0[b] = 4 * src;
 				}
 				if (s2 < nq) {
 					const uint32_t src = qlist[wq + s2];
-					a2[b] = __vsub4(__vcmpeq4(idn[src], m4) & 0x01010101u, __vcmpeq4(ido[src], m4) & 0x01010101u);
+					a2[b] = coef4(src);
 					off2[b] = 4 * src;
 				}
 			}
@@ -467,7 +496,7 @@ qvz_kmeans_assign_mma_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint
 			}
 		}
 		__syncthreads();                                 // the tile has been consumed
-		if (t + gridDim.x < tiles) fetch(t + gridDim.x);
+		if (t + (uint64_t) NBUF * gridDim.x < tiles) fetch(t + (uint64_t) NBUF * gridDim.x, buf);
 	}
 	__syncthreads();
 	for (uint32_t i = tid; i < K * ACCW; i += NT) {      // signed partials: sign-extend (two's complement add)
@@ -478,16 +507,16 @@ qvz_kmeans_assign_mma_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint
 	}
 }
 
-static size_t mma_smem(uint32_t K, uint32_t C4, uint32_t rows, uint32_t NT) {
+static size_t mma_smem(uint32_t K, uint32_t C4, uint32_t rows, uint32_t NT, uint32_t nbuf = 1) {
 	const uint32_t KP = (K + 3) & ~3u;
 	(void) NT;
-	return (4 + (size_t) C4 * (rows + 4) + (size_t) C4 * KP + (size_t) K * km_groups(C4) * 32 + KP + 3 * (rows / 4) + 8) * sizeof(uint32_t);
+	return (4 + (size_t) nbuf * C4 * (rows + 4) + (size_t) C4 * KP + (size_t) K * km_groups(C4) * 32 + KP + 3 * (rows / 4) + 8) * sizeof(uint32_t);
 }
 
-template <int KT, int NT, int RPT, bool FULL>
-static void launch_mma_nt(qvz_gpu *h, int64_t *target) {
-	auto kern = qvz_kmeans_assign_mma_kernel<KT, NT, RPT, FULL>;
-	const size_t smem = mma_smem(KT, h->L.C4, RPT * NT, NT);
+template <int KT, int NT, int RPT, bool FULL, int NBUF>
+static void launch_mma_nb(qvz_gpu *h, int64_t *target) {
+	auto kern = qvz_kmeans_assign_mma_kernel<KT, NT, RPT, FULL, NBUF>;
+	const size_t smem = mma_smem(KT, h->L.C4, RPT * NT, NT, NBUF);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	int per_sm = 0;
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
@@ -497,6 +526,13 @@ static void launch_mma_nt(qvz_gpu *h, int64_t *target) {
 	const uint64_t cap = (uint64_t) h->sm_count * per_sm;
 	kern<<<(unsigned) (blocks < cap ? blocks : cap), NT, smem, h->stream>>>(h->L, h->Xw, h->cl, h->means_t, h->means_sq,
 	                                                                       (unsigned long long *) target, h->km_ctl);
+}
+
+template <int KT, int NT, int RPT, bool FULL>
+static void launch_mma_nt(qvz_gpu *h, int64_t *target) {
+	const char *e = getenv("QVZ_KM_NBUF");           // 2: double-buffered tiles (half as many CTAs per SM)
+	if (e && atoi(e) == 2 && mma_smem(KT, h->L.C4, RPT * NT, NT, 2) <= 220 * 1024) launch_mma_nb<KT, NT, RPT, FULL, 2>(h, target);
+	else launch_mma_nb<KT, NT, RPT, FULL, 1>(h, target);
 }
 
 // shape of a tile: QVZ_KM_SHAPE = <rows per thread><threads>, e.g. 2128 = 2 rows x 128 threads (256-slot tiles, 4 warps)
@@ -513,6 +549,7 @@ static void launch_mma_shape(qvz_gpu *h, int64_t *target) {
 	case 432: launch_mma_nt<KT, 32, 4, FULL>(h, target); break;
 	case 2256: launch_mma_nt<KT, 256, 2, FULL>(h, target); break;
 	case 2128: launch_mma_nt<KT, 128, 2, FULL>(h, target); break;
+	case 1256: launch_mma_nt<KT, 256, 1, FULL>(h, target); break;
 	default: launch_mma_nt<KT, 64, 2, FULL>(h, target); break;
 	}
 }

@@ -78,7 +78,7 @@ def load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                 "(the qvz front end has no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(os.environ.get("QVZ_GPU_LIB", LIB_PATH))     # (QVZ_GPU_LIB: an experimental build of the same library)
     vp = C.c_void_p
     L.qvz_gpu_open.restype = C.c_int
     L.qvz_gpu_open.argtypes = [C.POINTER(vp), C.c_int]

@@ -95,8 +95,8 @@ def test_kmeans_and_counts_vs_oracle(gpu, oracle, n, c, k, thr):
     assert np.array_equal(gpu.cond_counts(), oracle.cond_counts(rows, c, k, o["ids"]))
 
 
-@pytest.mark.parametrize("shape", ["2128", "264", "2256", "464", "432", "sorted"])
-@pytest.mark.parametrize("n,c,k", [(70_000, 150, 5), (40_000, 250, 2), (33_333, 101, 8), (9000, 30, 3)])
+@pytest.mark.parametrize("shape", ["2128", "264", "2256", "464", "1256", "sorted"])
+@pytest.mark.parametrize("n,c,k", [(70_000, 150, 5), (40_000, 250, 2), (33_333, 101, 8)])
 def test_kmeans_kernel_variants(gpu, oracle, n, c, k, shape):
     """Every tile shape of the register-blocked k-means kernel (rows per thread x threads: tensor-core column sums,
     full and incremental iterations) and the counting-sort kernel give the oracle's ids, means, `moved` log and counts."""
