@@ -439,7 +439,9 @@ qvz_kmeans_assign_mma_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint
 		__syncwarp();
 		// lanes < QPW stand for this warp's quads of rows: a quad contributes to the sums if one of its rows changed cluster
 		// (measured alternatives: pooling the quads of all warps of the CTA so that late iterations run fewer, fuller batches
-		// gains 0.4-0.8 ms in the iterations where < 1 % of the rows move and loses 0.5-2.4 ms in all others)
+		// gains 0.4-0.8 ms in the iterations where < 1 % of the rows move and loses 0.5-2.4 ms in all others; so does a
+		// scalar path -- one shared atomic per byte -- for warps in which at most 1..4 rows moved: the mere presence of that
+		// code costs the other iterations 0.4-0.7 ms each)
 		const bool mine = lane < QPW && (FULL || idn[wq + lane] != ido[wq + lane]);
 		const uint32_t qmask = __ballot_sync(0xFFFFFFFFu, mine);
 		if (mine) qlist[wq + __popc(qmask & ((1u << lane) - 1))] = wq + lane;
@@ -464,7 +466,8 @@ qvz_kmeans_assign_mma_kernel(qvz_layout L, const uint32_t *__restrict__ Xw, uint
 					off2[b] = 4 * src;
 				}
 			}
-			for (uint32_t g = 0; g < G; ++g) {
+#pragma unroll 2
+			for (uint32_t g = 0; g < G; ++g) {           // (two groups in flight: the chain LDS -> PRMT -> IMMA -> ATOMS of one group is latency, not work)
 				const uint32_t c4 = 8 * g + (lane >> 2);
 				int c[4][4];
 #pragma unroll
