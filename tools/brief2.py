@@ -1,3 +1,4 @@
+"""One line per bench.py JSON output: value, step, stage times and per-kernel GB/s (dev helper)."""
 import json, sys
 for f in sys.argv[1:]:
     try:
