@@ -13,7 +13,12 @@
 //              sorted by cluster in shared memory and summed column-word-wise as packed 16-bit halves,
 //              CTA-level uint32 partials in shared memory, one 64-bit global atomic per (cluster, column,
 //              CTA).  Integer sums are order independent.
-//   recenter:  mean = (uint8)(sum / count), moved_k = sum (new-old)^2 -- tiny second kernel.
+//   recenter:  mean = (uint8)(sum / count), moved_k = sum (new-old)^2 -- tiny second kernel, which also evaluates
+//              do_kmeans_clustering's loop condition so that the host never waits for it.
+// Two implementations of the pass: up to 8 clusters (every BASELINE configuration) qvz_kmeans_assign_mma_kernel below --
+// register-blocked distances, column sums as small integer matrix products on the tensor cores, and from the second
+// iteration of a run on only the rows that changed cluster are added to / taken from the running sums; 9..16 clusters the
+// counting-sort kernel that follows (more: kmeans_wide.cu).
 #include <stdlib.h>
 
 #include <type_traits>

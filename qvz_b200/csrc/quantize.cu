@@ -291,8 +291,9 @@ int qvz_quantize_launch(qvz_gpu *h, int want_qv, int want_err, int dmode) {
 //                         threads are adjacent runs).  Line i of a run starts at draw i*C: the walk realigns.
 //   qvz_quantize_batched  one CTA walks QB_LINES slots column-synchronously.  The tables of a column are ONE
 //                         image of `rows` x A entries per plane, staged in shared memory by TMA bulk copies
-//                         (double buffered, mbarrier completion); each thread carries QB_LPT independent lines
-//                         (ILP across the dependent prev -> lookup -> prev chains).
+//                         (a ring of buffers, full/empty mbarriers); each thread carries QB_LPT independent lines
+//                         (ILP across the dependent prev -> lookup -> prev chains).  When no reachable context mixes
+//                         its two quantizers (DRAWS = false) the draws are neither generated nor read.
 //
 // Table image of a column (G[col] = two planes, lo quantizers then hi quantizers, of rows x A words):
 //   a ROW is one (cluster, context) pair that some line of the resident rows can reach in this column (row 0 is
