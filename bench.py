@@ -407,7 +407,9 @@ def run_native(args):
            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
            "config": {"workload": describe(cfg) + (f", cut into {world} contiguous shards of {n} lines" if world > 1 else ", one GPU"),
                       "lines_total": total, "lines_per_gpu": n, "columns": c, "clusters": k, "kmeans_iterations": iters,
-                      "tables": tables_kind, "resident": "rows and quantizer tables in HBM; WELL jump-ahead and draw generation inside the step",
+                      "tables": tables_kind,
+                      "resident": "rows and quantizer tables in HBM; " + ("WELL jump-ahead and draw generation inside the step" if stage["quantize_draws_ms"] > 0
+                                                                             else "no reachable context of these tables mixes its two quantizers, so the walk needs no WELL draws"),
                       "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2" % (n * c / 1e9),
                       "sharding": "contiguous line shards, NCCL all-reduce of int64 centroid sums and uint32 counts" if world > 1 else "single GPU"},
            "stage_ms": {kk: round(v, 4) for kk, v in stage.items()},
